@@ -1,0 +1,107 @@
+/*
+ * unmore_b200 — C ABI of the B200-native multi-object reasoning path of unMORE.
+ *
+ * The reference (vLAR-group/unMORE) is pure Python and has no FFI: the boundary it offers is
+ * the set of Python callables of object_reasoning.py / object_scoring.py / post_process.py.
+ * Each entry point below replaces the arithmetic of one of those callables (cited per
+ * function); unmore_b200/object_reasoning.py etc. keep the reference's Python signatures and
+ * forward here through ctypes.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates
+ *     device memory and keeps no pointer after returning;
+ *   - work is only enqueued on `stream` (a cudaStream_t); nothing synchronises the device;
+ *   - return value 0 = ok, otherwise a negative UNMORE_E_* code or a positive cudaError_t;
+ *     unmore_last_error() returns a thread-local description;
+ *   - fields: [n_img, C, H, W] fp32 contiguous; channel indices are passed explicitly
+ *     (the synthetic stacks use sdf=0, center_row=1, center_col=2, existence=3);
+ *   - proposal lists are ragged with a fixed capacity: boxes [n_img, cap, 4] xyxy, fp32 or
+ *     fp64 (boxes_f64 != 0; the reference hands fp64 anchors to round 0, object_reasoning.py
+ *     :190-194), image i owning the first counts[i] rows; counts == NULL means all cap rows;
+ *   - `ws` is a scheduling workspace of unmore_workspace_bytes(n_img) bytes.
+ *   - resize semantics: bilinear, align_corners=False, NO antialias (torchvision 0.14.1, the
+ *     version the reference pins), arithmetic bit-identical to ATen's CPU kernels.
+ */
+#ifndef UNMORE_B200_H_
+#define UNMORE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNMORE_E_INVALID (-1)   /* bad argument */
+#define UNMORE_E_CAPACITY (-2)  /* a capacity / size limit of the kernels is exceeded */
+
+typedef void* unmore_stream_t; /* cudaStream_t */
+
+const char* unmore_last_error(void);
+int unmore_version(void);
+/* bytes of the scheduling workspace `ws` used by the list-driven kernels */
+size_t unmore_workspace_bytes(int n_img);
+
+/* existence_checking — object_reasoning.py:491-523 (Binary_Classifier replaced by the mean of
+ * the resized crop's existence channel).  scores_out: [n_img, cap] fp32. */
+int unmore_existence_scores(const float* fields, int n_img, int C, int H, int W, int ch_exist,
+                            const void* boxes, int boxes_f64, const int* counts, int cap,
+                            float* scores_out, void* ws, unmore_stream_t stream);
+
+/* center_reasoning — object_reasoning.py:525-580 with batch_erode (utils/misc.py:10-20) and
+ * center_field_to_anti_center_map (object_reasoning.py:360-377) fused.
+ * max_values_out [n_img, cap] fp64: amax of the masked anti-center map;
+ * argmax_out [n_img, cap] int32: -1 if the proposal passes (max <= thr), else yc*128+xc;
+ * splits_out [n_img, cap, 4, 4] fp64 (nullable): left/right/top/bottom boxes of failing rows. */
+int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W, int ch_sdf,
+                            int ch_center_row, int ch_center_col, const void* boxes, int boxes_f64,
+                            const int* counts, int cap, double center_score_max_thres,
+                            double* max_values_out, int* argmax_out, double* splits_out, void* ws,
+                            unmore_stream_t stream);
+
+/* boundary_reasoning — object_reasoning.py:582-612: up to n_round rounds of
+ * filter_small_proposal (:293-299) + optimize_one_image_single_round (:379-487), one warp per
+ * proposal, box and label in registers, exit at the fixed point (label 1, box unchanged).
+ * With n_round=1, apply_small_filter=0 it is exactly optimize_one_image_single_round.
+ * boxes_out [n_img, cap, 4] fp32; labels_out [n_img, cap] fp32: 1 / 0 / -1 as the reference,
+ * -2 = removed by filter_small_proposal (not in the reference's returned list);
+ * rounds_out [n_img, cap] int32 (nullable): rounds actually evaluated. */
+int unmore_boundary_refine(const float* fields, int n_img, int C, int H, int W, int ch_sdf,
+                           const void* boxes, int boxes_f64, const int* counts, int cap, int n_round,
+                           int apply_small_filter, int early_exit, float proposal_area_thres,
+                           float max_sdf_thres, float max_shrink_threshold, float delta_ratio,
+                           float* boxes_out, float* labels_out, int* rounds_out, void* ws,
+                           unmore_stream_t stream);
+
+/* update_bbox_with_boundary_fields — object_reasoning.py:140-174 on pre-resampled tiles
+ * [M, 128, 128] fp32.  deltas_out [M, 4] = (delta_x1, delta_y1, delta_x2, delta_y2);
+ * max_out [M] (nullable) = amax of each tile. */
+int unmore_update_bbox_from_tiles(const float* tiles, int M, float* deltas_out, float* max_out,
+                                  unmore_stream_t stream);
+
+/* Order-preserving selection (the boolean-mask indexing of the reference, e.g.
+ * object_reasoning.py:422-426, 541-542, 630, 656).  For every image, entries e < count whose
+ * predicate holds are copied in order to out [n_img, cap_out, 4]; each entry carries `group`
+ * consecutive boxes (4 for the split lists).  mode: 0 pred=u8 flags; 1 pred=fp32 >= thr;
+ * 2 pred=fp32 == thr; 3 pred=int32 >= 0; 4 pred=int32 < 0.  append != 0 appends after the
+ * counts_out rows already present (torch.cat of two lists, :644).  index_out (nullable)
+ * [n_img, cap_out] receives the source entry index of each output row. */
+int unmore_compact_boxes(const void* in, int in_f64, const int* counts_in, int cap_in, int group,
+                         int mode, const void* pred, float thr, void* out, int out_f64, int cap_out,
+                         int* counts_out, int append, int* index_out, int n_img,
+                         unmore_stream_t stream);
+
+/* torchvision.ops.nms semantics — object_reasoning.py:661, object_scoring.py:238.
+ * boxes [n_img, cap, 4] fp32; scores [n_img, cap] fp32 or NULL (all equal: index order);
+ * keep_out [n_img, cap] int32 kept indices in descending-score order; keep_counts_out [n_img];
+ * boxes_out (nullable) [n_img, cap, 4] kept boxes in that order.
+ * order_ws: [n_img, cap] int32 scratch.  cap <= 32768. */
+int unmore_box_nms(const float* boxes, const float* scores, const int* counts, int cap, int n_img,
+                   float iou_threshold, int* keep_out, int* keep_counts_out, float* boxes_out,
+                   int* order_ws, unmore_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNMORE_B200_H_ */

@@ -1,0 +1,190 @@
+// center_reasoning (object_reasoning.py:525-580, analyze_cc off): per proposal, resample the
+// boundary-distance and the two center-field channels to 128x128, threshold them into a
+// union mask (sigmoid(sdf) > 0.5  OR  ||center|| > 0.5), erode it 3 x (9x9, zero border)
+// (utils/misc.py:10-20), evaluate the anti-center map (5x5 fp64 correlation, :360-377) on the
+// surviving pixels, and either pass the proposal (max <= thr) or split it at the arg-max.
+//
+// One CTA (512 threads) per proposal.  The mask lives as 128-bit rows; three 9x9 zero-border
+// erosions compose to a single 25x25 zero-border erosion, done with shift-AND doubling on
+// the packed rows and a 25-row AND.  Everything within 12 px of the crop border is eroded
+// away, which subsumes the reference's 10-px frame zeroing (:535-538), so only the central
+// 108x108 window of the center field (rows/cols 10..117) is ever read by the correlation:
+// that window is what is staged in shared memory (2 x 46,656 B -> two CTAs per SM).
+#include "resample.cuh"
+#include "unmore_internal.h"
+
+namespace unmore {
+
+constexpr int kCenterThreads = 512;
+constexpr int kCenterWarps = kCenterThreads / 32;
+constexpr int kWinLo = 10, kWinHi = 118, kWin = kWinHi - kWinLo;  // staged window of the center field
+constexpr int kErode = 12;                                         // 3 rounds x radius 4
+
+struct CenterSmem {
+  float c0[kWin * kWin];
+  float c1[kWin * kWin];
+  uint32_t mask[kCrop][4];   // union mask, bit j of row i = column j (LSB = lowest column)
+  uint32_t hrun[kCrop][4];   // horizontally eroded rows
+  uint32_t ero[kCrop][4];    // fully eroded mask
+  double red_val[kCenterWarps];
+  int red_idx[kCenterWarps];
+};
+
+typedef unsigned __int128 u128;
+
+__device__ __forceinline__ u128 load_row(const uint32_t r[4]) {
+  return ((u128)r[3] << 96) | ((u128)r[2] << 64) | ((u128)r[1] << 32) | (u128)r[0];
+}
+__device__ __forceinline__ void store_row(uint32_t r[4], u128 v) {
+  r[0] = (uint32_t)v; r[1] = (uint32_t)(v >> 32); r[2] = (uint32_t)(v >> 64); r[3] = (uint32_t)(v >> 96);
+}
+
+__global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CenterSmem& sm = *reinterpret_cast<CenterSmem*>(smem_raw);
+  __shared__ int s_id;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = worklist_total(p.work);
+  for (;;) {
+    if (tid == 0) s_id = atomicAdd(p.work.counter, 1);
+    __syncthreads();
+    const int id = s_id;
+    if (id >= total) break;
+    int img, k;
+    worklist_locate(p.work, id, img, k);
+    const size_t row = (size_t)img * p.work.cap + k;
+    double x1, y1, x2, y2;
+    load_box<double>(p.boxes, p.boxes_f64 != 0, row, x1, y1, x2, y2);
+    const Window win = snap_window<double>(x1, y1, x2, y2, p.W, p.H);
+    double best = 0.0;
+    int best_idx = -1;
+    if (!win.empty()) {
+      // ---- 1. resample 3 channels; warp w owns output rows 8w .. 8w+7
+      ColTaps taps;
+      taps.init(lane, win.w());
+      const size_t plane_sz = (size_t)p.H * p.W;
+      const float* base = p.fields + (size_t)img * p.C * plane_sz;
+      PlaneRows ps, p0, p1;
+      ps.init(base + p.ch_sdf * plane_sz, p.W, win);
+      p0.init(base + p.ch_crow * plane_sz, p.W, win);
+      p1.init(base + p.ch_ccol * plane_sz, p.W, win);
+      const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
+      const int in_h = win.h();
+      for (int ii = 0; ii < kCrop / kCenterWarps; ++ii) {
+        const int i = warp * (kCrop / kCenterWarps) + ii;
+        const AxisTap v = axis_tap(scale_y, i, in_h);
+        float s[4], a[4], b[4];
+        ps.row(taps, v, s);
+        p0.row(taps, v, a);
+        p1.row(taps, v, b);
+        uint32_t nib = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = 4 * lane + c;
+          // ||c|| > 0.5 exactly as torch.norm: round(a*a) + round(b*b), IEEE sqrt
+          const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c])));
+          const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (nrm > 0.5f);
+          nib |= (on ? 1u : 0u) << c;
+          if (i >= kWinLo && i < kWinHi && j >= kWinLo && j < kWinHi) {
+            sm.c0[(i - kWinLo) * kWin + (j - kWinLo)] = a[c];
+            sm.c1[(i - kWinLo) * kWin + (j - kWinLo)] = b[c];
+          }
+        }
+        // gather 8 lanes' nibbles into one 32-bit word (lanes 0, 8, 16, 24 end up holding words 0..3)
+        uint32_t w = nib;
+        w |= __shfl_down_sync(kFullMask, w, 1) << 4;
+        w |= __shfl_down_sync(kFullMask, w, 2) << 8;
+        w |= __shfl_down_sync(kFullMask, w, 4) << 16;
+        if ((lane & 7) == 0) sm.mask[i][lane >> 3] = w;
+      }
+      __syncthreads();
+      // ---- 2. erosion: 25-runs along rows, then AND of 25 rows
+      if (tid < kCrop) {
+        u128 m = load_row(sm.mask[tid]);
+        m &= m >> 1; m &= m >> 2; m &= m >> 4; m &= m >> 8;  // bit j: columns j..j+15 set
+        m &= m >> 9;                                          // bit j: columns j..j+24 set
+        store_row(sm.hrun[tid], m << kErode);                 // centre the run
+      }
+      __syncthreads();
+      if (tid < kCrop) {
+        u128 e = 0;
+        if (tid >= kErode && tid < kCrop - kErode) {
+          e = ~(u128)0;
+#pragma unroll 5
+          for (int d = -kErode; d <= kErode; ++d) e &= load_row(sm.hrun[tid + d]);
+        }
+        store_row(sm.ero[tid], e);
+      }
+      __syncthreads();
+      // ---- 3. anti-center map on surviving pixels, fp64, then masked max / first arg-max
+      constexpr int kInner = kCrop - 2 * kErode;  // 104: only rows/cols 12..115 can survive
+      double tbest = 0.0;
+      int tidx = -1;
+      for (int q = tid; q < kInner * kInner; q += kCenterThreads) {
+        const int r = kErode + q / kInner, c = kErode + q % kInner;
+        if (!((sm.ero[r][c >> 5] >> (c & 31)) & 1u)) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int di = 0; di < 5; ++di) {
+#pragma unroll
+          for (int dj = 0; dj < 5; ++dj) {
+            if (di == 2 && dj == 2) continue;
+            const int o = (r + di - 2 - kWinLo) * kWin + (c + dj - 2 - kWinLo);
+            acc = fma(p.filt[di * 5 + dj], (double)sm.c0[o], acc);   // f[0][i][j] = (2-i)/n
+            acc = fma(p.filt[dj * 5 + di], (double)sm.c1[o], acc);   // f[1][i][j] = (2-j)/n
+          }
+        }
+        acc = __ddiv_rn(acc, 24.0);
+        if (tidx < 0 || acc > tbest) { tbest = acc; tidx = r * kCrop + c; }  // q ascending == flat index ascending
+      }
+      // block arg-max, ties -> smallest flat index (torch.argmax returns the first maximum)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(kFullMask, tbest, o);
+        const int oi = __shfl_xor_sync(kFullMask, tidx, o);
+        if (oi >= 0 && (tidx < 0 || ov > tbest || (ov == tbest && oi < tidx))) { tbest = ov; tidx = oi; }
+      }
+      if (lane == 0) { sm.red_val[warp] = tbest; sm.red_idx[warp] = tidx; }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 0; w < kCenterWarps; ++w) {
+          const double ov = sm.red_val[w];
+          const int oi = sm.red_idx[w];
+          if (oi >= 0 && (best_idx < 0 || ov > best || (ov == best && oi < best_idx))) { best = ov; best_idx = oi; }
+        }
+      }
+    }
+    if (tid == 0) {
+      // amax over the whole map: pixels outside the eroded mask contribute 0
+      const double maxv = (best_idx >= 0 && best > 0.0) ? best : 0.0;
+      const bool pass = maxv <= p.thr;
+      p.max_values[row] = maxv;
+      p.argmax[row] = pass ? -1 : best_idx;
+      if (!pass && p.splits) {
+        const int yc = best_idx / kCrop, xc = best_idx % kCrop;
+        const double xr = (double)((float)xc / (float)kCrop), yr = (double)((float)yc / (float)kCrop);
+        const double xs = __dadd_rn(x1, __dmul_rn(__dsub_rn(x2, x1), xr));
+        const double ys = __dadd_rn(y1, __dmul_rn(__dsub_rn(y2, y1), yr));
+        double* o = p.splits + row * 16;
+        o[0] = x1; o[1] = y1; o[2] = xs; o[3] = y2;    // left   (:553)
+        o[4] = xs; o[5] = y1; o[6] = x2; o[7] = y2;    // right  (:554)
+        o[8] = x1; o[9] = y1; o[10] = x2; o[11] = ys;  // top    (:555)
+        o[12] = x1; o[13] = ys; o[14] = x2; o[15] = y2;  // bottom (:556)
+      }
+    }
+    __syncthreads();  // s_id and shared tiles are reused by the next proposal
+  }
+}
+
+int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  center_kernel<<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace unmore

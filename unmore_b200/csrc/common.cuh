@@ -1,0 +1,152 @@
+// Shared device helpers for the unMORE reasoning kernels (sm_100a).
+//
+// Arithmetic contract: the resampling helpers reproduce, bit for bit, the fp32
+// arithmetic of ATen's CPU bilinear kernels (torch 2.11, aten/src/ATen/native/cpu/
+// UpSampleKernel.cpp) that torchvision.transforms.Resize dispatches to at
+// object_reasoning.py:319,407,505 and object_scoring.py:131,206,222 — found by
+// experiment and pinned in tests/test_oracle_golden.py (oracle.resize_bilinear_np):
+//   scale = float(in) / float(out)
+//   src   = max(fma(scale, i + 0.5, -0.5), 0);  i0 = min(int(src), in-1);  i1 = i0 + (i0 < in-1)
+//   l1    = clamp(src - i0, 0, 1);  l0 = 1 - l1
+//   generic kernel (out_h + out_w > 128):
+//       t0 = fma(v00, w0, v01*w1); t1 = fma(v10, w0, v11*w1); out = fma(t0, h0, t1*h1)
+//   small-output kernel (out_h + out_w <= 128):
+//       out = fma(h1*w1, v11, fma(h1*w0, v10, fma(h0*w0, v00, (h0*w1)*v01)))
+// Explicit __fmul_rn/__fmaf_rn keep nvcc from re-associating or contracting differently.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace unmore {
+
+constexpr int kCrop = 128;                 // crop side hard-coded by the reference
+constexpr unsigned kFullMask = 0xffffffffu;
+// sigmoid(x) > 0.5 on the reference's CPU path  <=>  x > 1.5 * 2^-24 (0x33c00000); pinned in
+// tests/test_oracle_golden.py::test_sigmoid_threshold_constant
+#define UNMORE_SIGMOID_HALF_THRESHOLD 8.94069671630859375e-08f
+
+struct AxisTap {
+  int i0, i1;
+  float l0, l1;
+};
+
+__device__ __forceinline__ AxisTap axis_tap(float scale, int i, int in_size) {
+  float src = __fmaf_rn(scale, (float)i + 0.5f, -0.5f);
+  src = src < 0.f ? 0.f : src;
+  int i0 = (int)src;
+  i0 = i0 < in_size - 1 ? i0 : in_size - 1;
+  AxisTap t;
+  t.i0 = i0;
+  t.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  float l1 = __fsub_rn(src, (float)i0);
+  l1 = l1 < 0.f ? 0.f : (l1 > 1.f ? 1.f : l1);
+  t.l1 = l1;
+  t.l0 = __fsub_rn(1.f, l1);
+  return t;
+}
+
+// horizontal stage of the generic kernel: fma(v0, w0, v1*w1)
+__device__ __forceinline__ float lerp_h(float v0, float v1, float w0, float w1) {
+  return __fmaf_rn(v0, w0, __fmul_rn(v1, w1));
+}
+// vertical stage: fma(t0, h0, t1*h1)
+__device__ __forceinline__ float lerp_v(float t0, float t1, float h0, float h1) {
+  return __fmaf_rn(t0, h0, __fmul_rn(t1, h1));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Ragged work lists.  Boxes live in [n_img, cap, 4]; image i owns the first counts[i]
+// rows (counts == nullptr: all cap rows).  `offsets` (n_img+1 ints, exclusive prefix of
+// counts) is built by prefix_counts_kernel; warps pull flat item ids from an atomic
+// counter so long-running proposals (refine: 1..50 rounds) do not strand a CTA.
+// ---------------------------------------------------------------------------------------
+struct WorkList {
+  const int* offsets;  // n_img + 1, or nullptr when dense
+  int* counter;        // zeroed before launch
+  int n_img;
+  int cap;
+  int total_dense;     // n_img * cap when offsets == nullptr
+};
+
+__device__ __forceinline__ int worklist_total(const WorkList& w) {
+  return w.offsets ? __ldg(w.offsets + w.n_img) : w.total_dense;
+}
+
+// One lane fetches, all lanes get the id.
+__device__ __forceinline__ int worklist_next_warp(const WorkList& w) {
+  int id = 0;
+  if ((threadIdx.x & 31) == 0) id = atomicAdd(w.counter, 1);
+  return __shfl_sync(kFullMask, id, 0);
+}
+
+__device__ __forceinline__ void worklist_locate(const WorkList& w, int id, int& img, int& k) {
+  if (!w.offsets) {
+    img = id / w.cap;
+    k = id - img * w.cap;
+    return;
+  }
+  int lo = 0, hi = w.n_img;  // find img with offsets[img] <= id < offsets[img+1]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(w.offsets + mid) <= id) lo = mid; else hi = mid;
+  }
+  img = lo;
+  k = id - __ldg(w.offsets + lo);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_box(const void* boxes, bool f64, size_t row, T& x1, T& y1, T& x2, T& y2);
+
+template <>
+__device__ __forceinline__ void load_box<double>(const void* boxes, bool f64, size_t row, double& x1, double& y1,
+                                                 double& x2, double& y2) {
+  if (f64) {
+    const double4 b = reinterpret_cast<const double4*>(boxes)[row];
+    x1 = b.x; y1 = b.y; x2 = b.z; y2 = b.w;
+  } else {
+    const float4 b = reinterpret_cast<const float4*>(boxes)[row];
+    x1 = b.x; y1 = b.y; x2 = b.z; y2 = b.w;
+  }
+}
+
+// Crop window of a proposal: floor(x1), floor(y1), ceil(x2), ceil(y2)  (object_reasoning.py:404),
+// clamped to the image (the reference never produces out-of-range boxes: every producer clips).
+struct Window {
+  int x1, y1, x2, y2;
+  __device__ __forceinline__ int w() const { return x2 - x1; }
+  __device__ __forceinline__ int h() const { return y2 - y1; }
+  __device__ __forceinline__ bool empty() const { return x2 <= x1 || y2 <= y1; }
+};
+
+template <typename T>
+__device__ __forceinline__ Window snap_window(T x1, T y1, T x2, T y2, int W, int H) {
+  Window w;
+  w.x1 = max(0, min(W, (int)floor(x1)));
+  w.y1 = max(0, min(H, (int)floor(y1)));
+  w.x2 = max(0, min(W, (int)ceil(x2)));
+  w.y2 = max(0, min(H, (int)ceil(y2)));
+  return w;
+}
+
+}  // namespace unmore

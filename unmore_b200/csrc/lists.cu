@@ -1,0 +1,123 @@
+// Ragged-list plumbing: exclusive prefix of per-image counts (work scheduling) and the
+// order-preserving compactions that replace the reference's boolean-mask indexing
+// (e.g. object_reasoning.py:422-426, 541-542, 630, 656).  Order preservation matters: the
+// final discovery NMS has all-equal scores, so index order decides the keep-set (:661).
+#include "unmore_internal.h"
+
+namespace unmore {
+
+__global__ void prefix_counts_kernel(const int* __restrict__ counts, int n_img, int* __restrict__ offsets) {
+  // single CTA; n_img is small (images per launch)
+  __shared__ int carry;
+  __shared__ int wsum[32];
+  if (threadIdx.x == 0) { carry = 0; offsets[0] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_img; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int v = i < n_img ? counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(kFullMask, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int s = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, s, o);
+        if (lane >= o) s += y;
+      }
+      wsum[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    const int incl = x + (warp ? wsum[warp - 1] : 0) + carry;
+    if (i < n_img) offsets[i + 1] = incl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = incl;
+    __syncthreads();
+  }
+}
+
+int launch_prefix_counts(const int* counts, int n_img, int* offsets, cudaStream_t stream) {
+  prefix_counts_kernel<<<1, 1024, 0, stream>>>(counts, n_img, offsets);
+  return (int)cudaGetLastError();
+}
+
+__device__ __forceinline__ bool compact_pred(const CompactParams& p, size_t e) {
+  switch (p.mode) {
+    case kFlagsU8: return reinterpret_cast<const unsigned char*>(p.pred)[e] != 0;
+    case kScoreGE: return reinterpret_cast<const float*>(p.pred)[e] >= p.thr;
+    case kLabelEQ: return reinterpret_cast<const float*>(p.pred)[e] == p.thr;
+    case kArgmaxGE0: return reinterpret_cast<const int*>(p.pred)[e] >= 0;
+    default: return reinterpret_cast<const int*>(p.pred)[e] < 0;
+  }
+}
+
+// One CTA per image: block-wide stable stream compaction, `group` boxes per selected entry.
+__global__ void __launch_bounds__(1024) compact_kernel(const CompactParams p) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_in = p.counts_in ? p.counts_in[b] : p.cap_in;
+  const int base_out = p.append ? p.counts_out[b] : 0;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int start = 0; start < n_in; start += blockDim.x) {
+    const int e = start + threadIdx.x;
+    const size_t ge = (size_t)b * p.cap_in + e;
+    const bool sel = e < n_in && compact_pred(p, ge);
+    const unsigned bal = __ballot_sync(kFullMask, sel);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      int s = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, s, o);
+        if (lane >= o) s += y;
+      }
+      wsum[lane] = s;
+    }
+    __syncthreads();
+    const int rank = carry + (warp ? wsum[warp - 1] : 0) + within;
+    if (sel) {
+      for (int g = 0; g < p.group; ++g) {
+        const int orow = base_out + rank * p.group + g;
+        if (orow >= p.cap_out) break;
+        const size_t src = ge * p.group + g, dst = (size_t)b * p.cap_out + orow;
+        double v[4];
+        if (p.in_f64) {
+          const double4 t = reinterpret_cast<const double4*>(p.in)[src];
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+          const float4 t = reinterpret_cast<const float4*>(p.in)[src];
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+        if (p.out_f64) reinterpret_cast<double4*>(p.out)[dst] = make_double4(v[0], v[1], v[2], v[3]);
+        else reinterpret_cast<float4*>(p.out)[dst] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        if (p.index_out) p.index_out[dst] = e;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry += wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int n = base_out + carry * p.group;
+    p.counts_out[b] = n < p.cap_out ? n : p.cap_out;
+  }
+}
+
+int launch_compact(const CompactParams& p, cudaStream_t stream) {
+  if (p.n_img <= 0) return 0;
+  compact_kernel<<<p.n_img, 1024, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace unmore

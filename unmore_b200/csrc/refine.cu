@@ -1,0 +1,289 @@
+// Boundary reasoning: update_bbox_with_boundary_fields (object_reasoning.py:140-174),
+// optimize_one_image_single_round (:379-487) and the round loop of boundary_reasoning
+// (:582-612), fused into one persistent kernel.
+//
+// One warp owns one proposal for its whole life (<= n_round rounds): the box and label
+// stay in registers, each round re-snaps the crop window, resamples the boundary-distance
+// channel straight from the (L2-resident) field, reduces the soft-foreground/background
+// gradient averages, takes the four border maxima and applies the box update.  Proposals
+// are independent in the reference (no cross-proposal term anywhere in the loop), so the
+// per-round filter_small_proposal / boolean-mask compactions become per-proposal exits.
+#include "resample.cuh"
+#include "unmore_internal.h"
+
+namespace unmore {
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid as the soft foreground mask (object_reasoning.py:153); 2 MUFU + 2 FP32 ops
+__device__ __forceinline__ float soft_fg(float s) {
+  return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * s));
+}
+
+struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
+  const float* tile;
+  __device__ __forceinline__ void row(int lane, int i, float out[4]) const {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
+};
+
+struct CropRows {  // crop window of the boundary-distance channel, resampled on the fly
+  ColTaps taps;
+  PlaneRows plane;
+  float scale_y;
+  int in_h;
+  __device__ __forceinline__ void row(int /*lane*/, int i, float out[4]) {
+    plane.row(taps, axis_tap(scale_y, i, in_h), out);
+  }
+};
+
+// Per-warp scratch: S[i][0] and S[i][126] for i in [0,127) so the border pass needs no resample.
+struct BorderCols {
+  float left[kCrop];
+  float right[kCrop];
+};
+
+struct Deltas {
+  float max_sdf;
+  float dx1, dy1, dx2, dy2;
+};
+
+// a10 on one proposal.  `src.row(lane, i, out)` yields S[i][4*lane .. 4*lane+3].
+template <class RowSrc>
+__device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, int lane) {
+  float cur[4], nxt[4], top[4], bot[4];
+  src.row(lane, 0, cur);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) top[c] = cur[c];
+  float mx = fmaxf(fmaxf(cur[0], cur[1]), fmaxf(cur[2], cur[3]));
+  double dA = 0.0, dAg = 0.0, dB = 0.0, dBg = 0.0;
+  float fA = 0.f, fAg = 0.f, fB = 0.f, fBg = 0.f;
+  // fp32 partial sums are flushed into fp64 every 8 rows (32 px per lane): keeps the
+  // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
+  for (int i = 0; i < kCrop - 1; ++i) {
+    src.row(lane, i + 1, nxt);
+    const float right = __shfl_down_sync(kFullMask, cur[0], 1);
+    if (lane == 0) cols.left[i] = cur[0];
+    if (lane == 31) cols.right[i] = cur[2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float s = cur[c];
+      const float dxv = (c < 3 ? cur[c + 1] : right) - s;
+      const float dyv = nxt[c] - s;
+      // ||grad|| as torch.norm computes it: round(dy*dy) + round(dx*dx), then sqrt
+      const float g = sqrt_approx(__fadd_rn(__fmul_rn(dyv, dyv), __fmul_rn(dxv, dxv)));
+      const float a = soft_fg(s);
+      const float b = 1.f - a;
+      const bool valid = (c < 3) || (lane < 31);  // column 127 is outside the 127x127 region
+      if (valid) {
+        fA += a;
+        fAg = fmaf(a, g, fAg);
+        fB += b;
+        fBg = fmaf(b, g, fBg);
+      }
+      mx = fmaxf(mx, nxt[c]);
+    }
+    if ((i & 7) == 7 || i == kCrop - 2) {
+      dA += (double)fA; dAg += (double)fAg; dB += (double)fB; dBg += (double)fBg;
+      fA = fAg = fB = fBg = 0.f;
+    }
+    if (i == kCrop - 2) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bot[c] = cur[c];  // row 126
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+  }
+  Deltas d;
+  d.max_sdf = warp_max(mx);
+  const float sumA = (float)warp_sum(dA);
+  const float sumAg = (float)warp_sum(dAg);
+  const float sumB = (float)warp_sum(dB);
+  const float sumBg = (float)warp_sum(dBg);
+  // avg gradient norms and step sizes, fp32 like the reference (:155-158)
+  const float avg_fg = __fdiv_rn(sumAg, __fadd_rn(sumA, 1e-8f));
+  const float avg_bg = __fdiv_rn(sumBg, __fadd_rn(sumB, 1e-8f));
+  const float step_fg = __fdiv_rn(1.f, __fadd_rn(avg_fg, 1e-10f));
+  const float step_bg = __fdiv_rn(1.f, __fadd_rn(avg_bg, 1e-10f));
+  auto movement = [&](float s) {
+    const float a = soft_fg(s);
+    const float b = 1.f - a;
+    return __fmul_rn(__fadd_rn(__fmul_rn(step_fg, a), __fmul_rn(step_bg, b)), s);
+  };
+  __syncwarp();
+  float m_top = -INFINITY, m_bot = -INFINITY, m_left = -INFINITY, m_right = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < 3 || lane < 31) {
+      m_top = fmaxf(m_top, movement(top[c]));
+      m_bot = fmaxf(m_bot, movement(bot[c]));
+    }
+    const int i = lane + 32 * c;
+    if (i < kCrop - 1) {
+      m_left = fmaxf(m_left, movement(cols.left[i]));
+      m_right = fmaxf(m_right, movement(cols.right[i]));
+    }
+  }
+  __syncwarp();
+  d.dx1 = -warp_max(m_left);
+  d.dy1 = -warp_max(m_top);
+  d.dx2 = warp_max(m_right);
+  d.dy2 = warp_max(m_bot);
+  return d;
+}
+
+template <typename T>
+struct BoxT { T x1, y1, x2, y2; };
+
+// One round for one proposal, arithmetic in T (double on round 0 when the caller hands in
+// fp64 proposals — promotion at object_reasoning.py:190-194 — float afterwards).
+// Returns the label of this round and the updated box (fp32, :479).
+template <typename T>
+__device__ __forceinline__ int one_round(const RefineParams& p, const float* plane, BoxT<T> b, BorderCols& cols,
+                                         int lane, float4& out) {
+  out = make_float4(0.f, 0.f, 0.f, 0.f);
+  const Window win = snap_window<T>(b.x1, b.y1, b.x2, b.y2, p.W, p.H);
+  if (win.empty()) return -1;  // the reference would raise on a zero-size crop; defined as "no object"
+  CropRows src;
+  src.taps.init(lane, win.w());
+  src.plane.init(plane, p.W, win);
+  src.in_h = win.h();
+  src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
+  const Deltas d = boundary_terms(src, cols, lane);
+  if (!(d.max_sdf > p.max_sdf_thres)) return -1;
+  // signed deltas: >0 expands, <0 shrinks; expansion is ignored on sides glued to the image edge (:444-447)
+  float sg[4] = {-d.dx1, -d.dy1, d.dx2, d.dy2};
+  const bool edge[4] = {win.x1 == 0, win.y1 == 0, win.x2 == p.W, win.y2 == p.H};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (sg[k] > 0.f && edge[k]) sg[k] = 0.f;
+  const float max_exp = fmaxf(fmaxf(sg[0], sg[1]), fmaxf(sg[2], sg[3]));
+  const float max_shr = fminf(fminf(sg[0], sg[1]), fminf(sg[2], sg[3]));
+  const int label = (max_exp <= 0.f && max_shr >= -p.max_shrink_thres) ? 1 : 0;
+  // asymmetric step (:457-460): expansions x(1+ratio), shrinks x(1-ratio)
+  float dl[4];
+  dl[0] = __fsub_rn(d.dx1, __fmul_rn(fabsf(d.dx1), p.delta_ratio));
+  dl[1] = __fsub_rn(d.dy1, __fmul_rn(fabsf(d.dy1), p.delta_ratio));
+  dl[2] = __fadd_rn(d.dx2, __fmul_rn(fabsf(d.dx2), p.delta_ratio));
+  dl[3] = __fadd_rn(d.dy2, __fmul_rn(fabsf(d.dy2), p.delta_ratio));
+  if (label == 1) dl[0] = dl[1] = dl[2] = dl[3] = 0.f;
+  // post_process_bbox_update (:177-196): separate multiply and add, no contraction
+  T nx1, ny1, nx2, ny2;
+  if constexpr (sizeof(T) == 8) {
+    const double xr = __ddiv_rn(__dsub_rn(b.x2, b.x1), 128.0), yr = __ddiv_rn(__dsub_rn(b.y2, b.y1), 128.0);
+    nx1 = __dadd_rn(b.x1, __dmul_rn((double)dl[0], xr));
+    ny1 = __dadd_rn(b.y1, __dmul_rn((double)dl[1], yr));
+    nx2 = __dadd_rn(b.x2, __dmul_rn((double)dl[2], xr));
+    ny2 = __dadd_rn(b.y2, __dmul_rn((double)dl[3], yr));
+  } else {
+    const float xr = __fdiv_rn(__fsub_rn(b.x2, b.x1), 128.f), yr = __fdiv_rn(__fsub_rn(b.y2, b.y1), 128.f);
+    nx1 = __fadd_rn(b.x1, __fmul_rn(dl[0], xr));
+    ny1 = __fadd_rn(b.y1, __fmul_rn(dl[1], yr));
+    nx2 = __fadd_rn(b.x2, __fmul_rn(dl[2], xr));
+    ny2 = __fadd_rn(b.y2, __fmul_rn(dl[3], yr));
+  }
+  if (nx1 < (T)0) nx1 = (T)0;
+  if (ny1 < (T)0) ny1 = (T)0;
+  if (nx2 > (T)p.W) nx2 = (T)p.W;
+  if (ny2 > (T)p.H) ny2 = (T)p.H;
+  out = make_float4((float)nx1, (float)ny1, (float)nx2, (float)ny2);
+  return label;
+}
+
+constexpr int kRefineWarps = 8;
+
+__global__ void __launch_bounds__(kRefineWarps * 32) refine_kernel(const RefineParams p) {
+  __shared__ BorderCols cols_all[kRefineWarps];
+  const int lane = threadIdx.x & 31;
+  BorderCols& cols = cols_all[threadIdx.x >> 5];
+  const int total = worklist_total(p.work);
+  for (;;) {
+    const int id = worklist_next_warp(p.work);
+    if (id >= total) break;
+    int img, k;
+    worklist_locate(p.work, id, img, k);
+    const size_t row = (size_t)img * p.work.cap + k;
+    const float* plane = p.fields + ((size_t)img * p.C + p.ch_sdf) * p.H * p.W;
+    BoxT<double> bd;
+    load_box<double>(p.boxes, p.boxes_f64 != 0, row, bd.x1, bd.y1, bd.x2, bd.y2);
+    BoxT<float> bf = {(float)bd.x1, (float)bd.y1, (float)bd.x2, (float)bd.y2};
+    float4 cur = make_float4(bf.x1, bf.y1, bf.x2, bf.y2);
+    float label = 0.f;
+    int rounds = 0;
+    for (int r = 0; r < p.n_round; ++r) {
+      const bool dbl = (r == 0) && p.boxes_f64;
+      if (p.apply_small_filter) {  // filter_small_proposal (:293-299), strict '>'
+        bool keep;
+        if (dbl) keep = __dmul_rn(__dsub_rn(bd.x2, bd.x1), __dsub_rn(bd.y2, bd.y1)) > (double)p.area_thres;
+        else keep = __fmul_rn(__fsub_rn(bf.x2, bf.x1), __fsub_rn(bf.y2, bf.y1)) > p.area_thres;
+        if (!keep) { label = -2.f; break; }
+      }
+      float4 nb;
+      const int lab = dbl ? one_round<double>(p, plane, bd, cols, lane, nb) : one_round<float>(p, plane, bf, cols, lane, nb);
+      rounds = r + 1;
+      label = (float)lab;
+      // fp64 round 0: the fp32 cast must be exact and the fp32 area test of round 1 must agree
+      const bool fixed = lab == 1 && nb.x == cur.x && nb.y == cur.y && nb.z == cur.z && nb.w == cur.w &&
+                         (!dbl || ((double)nb.x == bd.x1 && (double)nb.y == bd.y1 && (double)nb.z == bd.x2 &&
+                                   (double)nb.w == bd.y2 &&
+                                   (!p.apply_small_filter ||
+                                    __fmul_rn(__fsub_rn(nb.z, nb.x), __fsub_rn(nb.w, nb.y)) > p.area_thres)));
+      cur = nb;
+      bf.x1 = nb.x; bf.y1 = nb.y; bf.x2 = nb.z; bf.y2 = nb.w;
+      // label 1 with an unchanged box is an exact fixed point of the remaining rounds
+      // (same window, same field, same arithmetic); label -1 leaves a zero box that the
+      // next round's area filter removes
+      if (p.early_exit && fixed) break;
+      if (lab < 0 && p.apply_small_filter && p.area_thres >= 0.f) {
+        if (r + 1 < p.n_round) label = -2.f;
+        break;
+      }
+    }
+    if (lane == 0) {
+      p.boxes_out[row] = cur;
+      p.labels_out[row] = label;
+      if (p.rounds_out) p.rounds_out[row] = rounds;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRefineWarps * 32) tiles_kernel(const TileParams p) {
+  __shared__ BorderCols cols_all[kRefineWarps];
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRefineWarps + (threadIdx.x >> 5);
+  if (warp >= p.M) return;
+  TileRows src{p.tiles + (size_t)warp * kCrop * kCrop};
+  const Deltas d = boundary_terms(src, cols_all[threadIdx.x >> 5], lane);
+  if (lane == 0) {
+    p.deltas[warp] = make_float4(d.dx1, d.dy1, d.dx2, d.dy2);
+    if (p.max_sdf) p.max_sdf[warp] = d.max_sdf;
+  }
+}
+
+int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream) {
+  const int ctas = num_sms * 4;  // 32 warps/SM resident; warps pull proposals dynamically
+  refine_kernel<<<ctas, kRefineWarps * 32, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int launch_tiles(const TileParams& p, cudaStream_t stream) {
+  if (p.M <= 0) return 0;
+  tiles_kernel<<<(p.M + kRefineWarps - 1) / kRefineWarps, kRefineWarps * 32, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace unmore

@@ -1,0 +1,66 @@
+// Warp-cooperative crop + bilinear resample to 128x128 ("a2", object_reasoning.py:402-410).
+//
+// Mapping: one warp per proposal; lane l owns the four contiguous output columns
+// 4l..4l+3 of every output row.  Horizontal interpolation of a source row is kept in
+// registers and reused while consecutive output rows hit the same source rows (always
+// the case when the crop is smaller than 128 px high), so an up-sampled crop costs
+// in_h * 8 loads per lane instead of 128 * 16.
+#pragma once
+#include "common.cuh"
+
+namespace unmore {
+
+// Column taps of this lane for the current window (shared by all channels).
+struct ColTaps {
+  int x0[4], x1[4];
+  float w0[4], w1[4];
+  __device__ __forceinline__ void init(int lane, int in_w) {
+    const float scale = __fdiv_rn((float)in_w, (float)kCrop);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      AxisTap t = axis_tap(scale, 4 * lane + c, in_w);
+      x0[c] = t.i0; x1[c] = t.i1; w0[c] = t.l0; w1[c] = t.l1;
+    }
+  }
+};
+
+// One channel plane of one window, with a two-row cache of horizontally interpolated rows.
+struct PlaneRows {
+  const float* origin;  // &plane[y1 * W + x1]
+  int stride;           // W
+  int cy0, cy1;         // source rows held in ra / rb (-1: none)
+  float ra[4], rb[4];
+
+  __device__ __forceinline__ void init(const float* plane, int W, const Window& win) {
+    origin = plane + (size_t)win.y1 * W + win.x1;
+    stride = W;
+    cy0 = cy1 = -1;
+  }
+  __device__ __forceinline__ void hrow(const ColTaps& t, int y, float out[4]) const {
+    const float* p = origin + (size_t)y * stride;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = lerp_h(__ldg(p + t.x0[c]), __ldg(p + t.x1[c]), t.w0[c], t.w1[c]);
+  }
+  // S[i][4l..4l+3] for the output row whose vertical tap is `v`
+  __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[4]) {
+    if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
+      if (v.i0 == cy1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ra[c] = rb[c];
+      } else {
+        hrow(t, v.i0, ra);
+      }
+      if (v.i1 == v.i0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rb[c] = ra[c];
+      } else {
+        hrow(t, v.i1, rb);
+      }
+      cy0 = v.i0; cy1 = v.i1;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = lerp_v(ra[c], rb[c], v.l0, v.l1);
+  }
+};
+
+}  // namespace unmore

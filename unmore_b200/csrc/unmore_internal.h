@@ -1,0 +1,105 @@
+// Internal launch interfaces between the C-ABI translation unit (capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace unmore {
+
+struct FieldDesc {
+  const float* data;  // [n_img, C, H, W] fp32 contiguous
+  int n_img, C, H, W;
+};
+
+// ---- refine.cu -----------------------------------------------------------------------
+struct RefineParams {
+  const float* fields;
+  int C, H, W, ch_sdf;
+  const void* boxes;  // [n_img, cap, 4] fp32 or fp64
+  int boxes_f64;
+  WorkList work;
+  int n_round;
+  int apply_small_filter;  // filter_small_proposal before every round (boundary_reasoning) or not (single round)
+  int early_exit;
+  float area_thres, max_sdf_thres, max_shrink_thres, delta_ratio;
+  float4* boxes_out;   // [n_img, cap]
+  float* labels_out;   // 1 / 0 / -1 as the reference; -2 = removed by filter_small_proposal
+  int* rounds_out;     // rounds actually evaluated (nullable)
+};
+struct TileParams {
+  const float* tiles;  // [M, 128, 128]
+  int M;
+  float4* deltas;      // [M] (dx1, dy1, dx2, dy2)
+  float* max_sdf;      // [M] or nullptr
+};
+int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream);
+int launch_tiles(const TileParams& p, cudaStream_t stream);
+
+// ---- exist.cu ------------------------------------------------------------------------
+struct ExistParams {
+  const float* fields;
+  int C, H, W, ch_exist;
+  const void* boxes;
+  int boxes_f64;
+  WorkList work;
+  float* scores;  // [n_img, cap]
+};
+int launch_existence(const ExistParams& p, int num_sms, cudaStream_t stream);
+
+// ---- center.cu -----------------------------------------------------------------------
+struct CenterParams {
+  const float* fields;
+  int C, H, W, ch_sdf, ch_crow, ch_ccol;
+  const void* boxes;
+  int boxes_f64;
+  WorkList work;
+  double thr;          // center_score_max_thres
+  double* max_values;  // [n_img, cap] amax of the masked anti-center map (fp64)
+  int* argmax;         // [n_img, cap] flat index yc*128+xc of the first maximum, -1 when the proposal passes
+  double* splits;      // [n_img, cap, 4, 4] L/R/T/B boxes for failing proposals (nullable)
+  // F.normalize(filter, dim=1) in fp32, then .double() (object_reasoning.py:372-373):
+  // filt[i*5+j] = (2-i)/sqrt((2-i)^2+(2-j)^2); channel 1 uses the transposed entry
+  double filt[25];
+};
+int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream);
+
+// ---- lists.cu ------------------------------------------------------------------------
+int launch_prefix_counts(const int* counts, int n_img, int* offsets, cudaStream_t stream);
+
+enum CompactMode { kFlagsU8 = 0, kScoreGE = 1, kLabelEQ = 2, kArgmaxGE0 = 3, kArgmaxLT0 = 4 };
+struct CompactParams {
+  const void* in;        // [n_img, cap_in, group, 4]
+  int in_f64;
+  const int* counts_in;  // nullable
+  int cap_in;
+  int group;             // boxes per entry (1, or 4 for split boxes)
+  int mode;
+  const void* pred;      // u8 flags / float scores / float labels / int argmax, [n_img, cap_in]
+  float thr;
+  void* out;             // [n_img, cap_out, 4]
+  int out_f64;
+  int cap_out;
+  int* counts_out;       // [n_img]
+  int append;            // 1: append after the counts_out[] rows already present
+  int* index_out;        // nullable [n_img, cap_out]: source entry index of every output row
+  int n_img;
+};
+int launch_compact(const CompactParams& p, cudaStream_t stream);
+
+// ---- nms.cu --------------------------------------------------------------------------
+struct NmsParams {
+  const float4* boxes;   // [n_img, cap]
+  const float* scores;   // [n_img, cap] or nullptr (all equal -> index order)
+  const int* counts;     // nullable
+  int cap, n_img;
+  float iou_thr;
+  int* keep;             // [n_img, cap] kept indices in descending-score order
+  int* keep_counts;      // [n_img]
+  float4* boxes_out;     // nullable [n_img, cap] kept boxes, same order
+  int* order_ws;         // [n_img, cap] workspace
+  unsigned char* alive_ws;  // [n_img, cap] workspace
+};
+int launch_box_nms(const NmsParams& p, cudaStream_t stream);
+
+}  // namespace unmore

@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's ``object_reasoning.py`` (class ``Object_Discovery``).
+
+Method names, argument order, return containers and dict keys follow the reference
+(object_reasoning.py:43-665); the arithmetic runs in libunmore_b200.so on the GPU.  The
+one deliberate difference is the producer boundary: the reference runs its nets on every
+crop, every round (:398-417); here ``image`` is the per-image ``[4, H, W]`` field stack the
+objectness net produced once ([sdf, center_row, center_col, existence]) and the kernels
+resample it per proposal — SURVEY.md §0 "field-stub bridge".
+
+``discover_batch`` is the batched, sync-free form of ``main_object_discovery``'s loop body
+used by bench.py and the multi-GPU sharder: many images per launch, ragged lists with
+device-side counts, no host round-trips between stages.
+"""
+from __future__ import annotations
+
+import argparse
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .synth import anchor_proposals
+
+HYPER_DEFAULTS = dict(  # object_reasoning.py:700-707
+    class_score_thres=0.1, center_score_max_thres=0.009, analyze_cc=False, max_sdf_thres=0.5,
+    max_shrink_threshold=16, delta_ratio=0.5, n_round=50, proposal_area_thres=50, seed=0)
+
+
+def default_args(**over) -> argparse.Namespace:
+    d = dict(HYPER_DEFAULTS)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+class Object_Discovery:
+    def __init__(self, args: Optional[argparse.Namespace] = None, device=None, channels: ops.Channels = ops.DEFAULT_CHANNELS):
+        self.args = args if args is not None else default_args()
+        for k, v in HYPER_DEFAULTS.items():
+            if not hasattr(self.args, k):
+                setattr(self.args, k, v)
+        if getattr(self.args, "analyze_cc", False):
+            raise NotImplementedError("--analyze_cc (connected components, object_reasoning.py:561-572) "
+                                      "is not on the CUDA path yet (SURVEY.md §8f rank 3)")
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise RuntimeError("unmore_b200 has no CPU path; pass a CUDA device")
+        self.channels = channels
+        self.height = None
+        self.width = None
+
+    # ---- a1 ---------------------------------------------------------------------------
+    @staticmethod
+    def generate_random_proposal(height, width):
+        """object_reasoning.py:110-137 — float64 [N,4] anchors (host side, negligible cost)."""
+        return anchor_proposals(height, width)
+
+    # ---- helpers ----------------------------------------------------------------------
+    def _fields(self, image: torch.Tensor) -> torch.Tensor:
+        f = image.to(self.device, torch.float32)
+        if f.dim() == 3:
+            f = f.unsqueeze(0)
+        return f.contiguous()
+
+    def _boxes(self, proposals) -> torch.Tensor:
+        if not torch.is_tensor(proposals):
+            proposals = torch.as_tensor(np.asarray(proposals))
+        if proposals.numel() == 0:
+            return torch.zeros((1, 0, 4), dtype=torch.float64, device=self.device)
+        if proposals.dtype not in (torch.float32, torch.float64):
+            proposals = proposals.to(torch.float64)
+        return proposals.to(self.device).reshape(1, -1, 4).contiguous()
+
+    # ---- a3 ---------------------------------------------------------------------------
+    def existence_checking(self, image, proposals) -> Dict[str, torch.Tensor]:
+        """object_reasoning.py:491-523 — {'existence_scores': [N] fp32 on CPU}."""
+        boxes = self._boxes(proposals)
+        if boxes.shape[1] == 0:
+            return {"existence_scores": torch.zeros((0,), dtype=torch.float32)}
+        scores = ops.existence_scores(self._fields(image), boxes, ch=self.channels)
+        return {"existence_scores": scores[0].cpu()}
+
+    # ---- a7 ---------------------------------------------------------------------------
+    def center_reasoning(self, image, proposals) -> Dict[str, torch.Tensor]:
+        """object_reasoning.py:525-580 — {'proposals_pass_singularity', 'splited_new_proposals'}
+        (an empty float64 [0,4] tensor where the reference leaves an empty list)."""
+        boxes = self._boxes(proposals)
+        if boxes.shape[1] == 0:
+            e = torch.zeros((0, 4), dtype=torch.float64, device=self.device)
+            return {"proposals_pass_singularity": e, "splited_new_proposals": e.clone()}
+        _, argmax, splits = ops.center_reasoning(self._fields(image), boxes, thr=self.args.center_score_max_thres,
+                                                 ch=self.channels)
+        fail = argmax[0] >= 0
+        return {"proposals_pass_singularity": boxes[0][~fail],
+                "splited_new_proposals": splits[0][fail].reshape(-1, 4)}
+
+    # ---- a9 ---------------------------------------------------------------------------
+    def filter_small_proposal(self, proposals, labels):
+        """object_reasoning.py:293-299 (plain tensor indexing; the fused loop does this on device)."""
+        area = (proposals[:, 2] - proposals[:, 0]) * (proposals[:, 3] - proposals[:, 1])
+        keep = area > self.args.proposal_area_thres
+        return proposals[keep], labels[keep]
+
+    # ---- a10 / a12 --------------------------------------------------------------------
+    @staticmethod
+    def update_bbox_with_boundary_fields(sdf_maps):
+        """object_reasoning.py:140-174 on [B,128,128] CUDA tiles -> (dx1, dy1, dx2, dy2)."""
+        deltas, _ = ops.update_bbox_from_tiles(sdf_maps)
+        return deltas[:, 0], deltas[:, 1], deltas[:, 2], deltas[:, 3]
+
+    @staticmethod
+    def post_process_bbox_update(original_bboxes, delta_bboxes, delta_scale_x=128, delta_scale_y=128):
+        """object_reasoning.py:177-196 — four elementwise ops; kept in torch (fused on device inside
+        the refine kernel, this entry point exists for signature parity)."""
+        xr = (original_bboxes[:, 2] - original_bboxes[:, 0]) / delta_scale_x
+        yr = (original_bboxes[:, 3] - original_bboxes[:, 1]) / delta_scale_y
+        out = original_bboxes.clone()
+        out[:, 0] = original_bboxes[:, 0] + delta_bboxes[:, 0] * xr
+        out[:, 1] = original_bboxes[:, 1] + delta_bboxes[:, 1] * yr
+        out[:, 2] = original_bboxes[:, 2] + delta_bboxes[:, 2] * xr
+        out[:, 3] = original_bboxes[:, 3] + delta_bboxes[:, 3] * yr
+        return out
+
+    # ---- a11 --------------------------------------------------------------------------
+    def optimize_one_image_single_round(self, image, proposals, labels=None) -> Dict[str, torch.Tensor]:
+        """object_reasoning.py:379-487 — {'updated_bboxes': [N,4] fp32, 'labels': [N] fp32}."""
+        boxes = self._boxes(proposals)
+        if boxes.shape[1] == 0:
+            return {"updated_bboxes": torch.zeros((0, 4), dtype=torch.float32, device=self.device),
+                    "labels": torch.zeros((0,), dtype=torch.float32, device=self.device)}
+        a = self.args
+        out, lab, _ = ops.boundary_refine(self._fields(image), boxes, n_round=1, apply_small_filter=False,
+                                          early_exit=False, proposal_area_thres=a.proposal_area_thres,
+                                          max_sdf_thres=a.max_sdf_thres, max_shrink_threshold=a.max_shrink_threshold,
+                                          delta_ratio=a.delta_ratio, ch=self.channels)
+        return {"updated_bboxes": out[0], "labels": lab[0]}
+
+    # ---- a13 --------------------------------------------------------------------------
+    def boundary_reasoning(self, image, proposals, n_round=50):
+        """object_reasoning.py:582-612.  Like the reference the loop length is ``args.n_round``
+        (the parameter is ignored there too, :592).  Returns the rows still in the list after
+        the last round — label -1 rows of the last round included as zero boxes."""
+        boxes = self._boxes(proposals)
+        if boxes.shape[1] == 0:
+            return {"proposals": [], "labels": []}
+        a = self.args
+        out, lab, _ = ops.boundary_refine(self._fields(image), boxes, n_round=a.n_round, apply_small_filter=True,
+                                          early_exit=True, proposal_area_thres=a.proposal_area_thres,
+                                          max_sdf_thres=a.max_sdf_thres, max_shrink_threshold=a.max_shrink_threshold,
+                                          delta_ratio=a.delta_ratio, ch=self.channels)
+        in_list = lab[0] > -2
+        if int(in_list.sum()) == 0:
+            return {"proposals": [], "labels": []}
+        return {"proposals": out[0][in_list], "labels": lab[0][in_list]}
+
+    # ---- main loop body ---------------------------------------------------------------
+    def discover_image(self, image, proposals=None) -> np.ndarray:
+        """Loop body of main_object_discovery (object_reasoning.py:618-662) for one image:
+        final [K,4] fp32 boxes (empty where the reference ``continue``s)."""
+        f = self._fields(image)
+        if proposals is None:
+            proposals = self.generate_random_proposal(f.shape[-2], f.shape[-1])
+        boxes = self._boxes(proposals)
+        det, cnt = self.discover_batch(f, boxes)
+        return det[0, : int(cnt[0])].cpu().numpy()
+
+    def discover_batch(self, fields: torch.Tensor, proposals: torch.Tensor, counts: Optional[torch.Tensor] = None,
+                       stats: Optional[dict] = None):
+        """Existence check -> center reasoning -> re-check of the splits -> boundary reasoning ->
+        NMS for a batch of images, entirely on device.
+
+        fields [B,4,H,W] fp32, proposals [B,N,4] fp64/fp32, counts [B] int32 or None.
+        Returns (boxes [B, 5N, 4] fp32, counts [B] int32) in the reference's output order."""
+        a = self.args
+        ch = self.channels
+        B, N = proposals.shape[0], proposals.shape[1]
+        dev = fields.device
+        f64 = torch.float64
+        ws = ops.workspace(B, dev)
+        # Step 1: existence checking (:627-630)
+        ex = ops.existence_scores(fields, proposals, counts, ch=ch, ws=ws)
+        p1, c1, _ = ops.compact_boxes(proposals, counts, ops.MODE_SCORE_GE, ex, thr=a.class_score_thres, out_dtype=f64)
+        # Step 2: center reasoning (:634-637)
+        _, am1, sp1 = ops.center_reasoning(fields, p1, c1, thr=a.center_score_max_thres, ch=ch, ws=ws)
+        cap_out = 5 * N
+        refine_in = torch.zeros((B, cap_out, 4), dtype=f64, device=dev)
+        rc = torch.zeros((B,), dtype=torch.int32, device=dev)
+        ops.compact_boxes(p1, c1, ops.MODE_ARGMAX_LT0, am1, out=refine_in, counts_out=rc)
+        split, sc, _ = ops.compact_boxes(sp1, c1, ops.MODE_ARGMAX_GE0, am1, group=4, out_dtype=f64)
+        # re-check the split proposals (:639-646)
+        ex2 = ops.existence_scores(fields, split, sc, ch=ch, ws=ws)
+        p2, c2, _ = ops.compact_boxes(split, sc, ops.MODE_SCORE_GE, ex2, thr=a.class_score_thres, out_dtype=f64)
+        _, am2, _ = ops.center_reasoning(fields, p2, c2, thr=a.center_score_max_thres, ch=ch, ws=ws, want_splits=False)
+        ops.compact_boxes(p2, c2, ops.MODE_ARGMAX_LT0, am2, out=refine_in, counts_out=rc, append=True)
+        # Step 3: boundary reasoning (:650-658)
+        rb, lab, rounds = ops.boundary_refine(fields, refine_in, rc, n_round=a.n_round, apply_small_filter=True,
+                                              early_exit=True, proposal_area_thres=a.proposal_area_thres,
+                                              max_sdf_thres=a.max_sdf_thres,
+                                              max_shrink_threshold=a.max_shrink_threshold, delta_ratio=a.delta_ratio,
+                                              ch=ch, ws=ws, want_rounds=stats is not None)
+        fin, fc, _ = ops.compact_boxes(rb, rc, ops.MODE_LABEL_EQ, lab, thr=1.0, out_dtype=torch.float32)
+        # NMS with all-equal scores (:661): index order decides
+        _, kc, kb = ops.box_nms(fin, None, fc, iou_threshold=0.5)
+        if stats is not None:
+            stats.update(existence_in=counts, pass1=c1, split=sc, split_kept=c2, refine_in=rc, refine_rounds=rounds,
+                         label1=fc, kept=kc, existence_scores=ex, refine_boxes=rb, refine_labels=lab,
+                         refine_in_boxes=refine_in, pass1_boxes=p1, argmax1=am1)
+        return kb, kc
+
+    def main_object_discovery(self, images, image_ids, proposals=None) -> Dict[int, np.ndarray]:
+        """object_reasoning.py:615-665 over an in-memory list of field stacks: returns
+        ``results_dict`` {image_id: [K,4] fp32}; images with no detection are absent."""
+        results = {}
+        for img, iid in zip(images, image_ids):
+            det = self.discover_image(img, proposals)
+            if len(det):
+                results[int(iid)] = det
+        return results
