@@ -101,6 +101,71 @@ int unmore_box_nms(const float* boxes, const float* scores, const int* counts, i
                    float iou_threshold, int* keep_out, int* keep_counts_out, float* boxes_out,
                    int* order_ws, unmore_stream_t stream);
 
+/* batch_erode — utils/misc.py:10-20 on [B, 128, 128] u8 masks (non-zero = set): num_round
+ * erosions with a kernel_size x kernel_size ones kernel and zero border.  out: u8 {0,1}. */
+int unmore_batch_erode(const unsigned char* masks, int B, int H, int W, int kernel_size, int num_round,
+                       unsigned char* out, unmore_stream_t stream);
+
+/* center_field_to_anti_center_map — object_reasoning.py:360-377: vote_maps [B, 2, H, W] fp32 ->
+ * out [B, H, W] fp64 (5x5 normalised "points-at-me" correlation, zero padding, / 24). */
+int unmore_anti_center_map(const float* vote_maps, int B, int H, int W, int kernel_size, double* out,
+                           unmore_stream_t stream);
+
+/* Large-K variant of unmore_box_nms for ONE list of K boxes (config "NMS sweep, 1k-16k"):
+ * stable rank sort -> 64-wide suppression bit-matrix -> single-warp greedy scan.  Same results.
+ * order_ws [K] int32; matrix_ws [K * ceil(K/64)] u64; keep_out [K]; keep_count_out [1]. */
+int unmore_box_nms_matrix(const float* boxes, const float* scores, int K, float iou_threshold,
+                          int* order_ws, void* matrix_ws, int* keep_out, int* keep_count_out,
+                          unmore_stream_t stream);
+
+/* main_object_scoring steps 1-6 — object_scoring.py:182-235: per box the existence / center /
+ * boundary scores, the union of the two binary masks resized back to the box (bilinear +
+ * round-half-even, :196-228), its tight box (pycocotools toBbox semantics, :160-164) and area.
+ * scores_out [n_img, cap, 4] fp32 = (existence, center, boundary, 0);
+ * tight_out [n_img, cap, 4] fp32 xyxy (zeros for an empty mask); areas_out [n_img, cap] int32;
+ * masks_out (nullable) [n_img, cap, H, ceil(W/32)] u32, LSB = lowest x. */
+int unmore_score_and_rasterise(const float* fields, int n_img, int C, int H, int W, int ch_sdf,
+                               int ch_center_row, int ch_center_col, int ch_exist, const void* boxes,
+                               int boxes_f64, const int* counts, int cap, float* scores_out,
+                               float* tight_out, int* areas_out, uint32_t* masks_out,
+                               unmore_stream_t stream);
+
+/* main_object_scoring steps 7b-8 (object_scoring.py:244-266) + the post_process predicate
+ * (post_process.py:61-74) for the detections kept by the second NMS, in keep order:
+ * out [n_img, cap, 5] fp64 = (score, existence_score, center_score, boundary_score, area_score);
+ * bbox_xywh_out [n_img, cap, 4] fp32 COCO box; selected_out (nullable) [n_img, cap] u8 = 1 unless
+ * existence < t_e or center < t_c or boundary < t_b. */
+int unmore_final_scores(const float* scores, const float* tight, const int* areas, const int* keep,
+                        const int* keep_counts, int cap, int n_img, float existence_score_thres,
+                        float center_score_thres, float boundary_score_thres, double* out,
+                        float* bbox_xywh_out, unsigned char* selected_out, unmore_stream_t stream);
+
+/* Summed-area tables (north-star op (a); no reference counterpart, oracle = fp64 cumsum):
+ * in [n_planes, H, W] fp32 -> out [n_planes, H+1, W+1] fp64, out[y][x] = sum in[:y, :x]. W <= 2048. */
+int unmore_sat_build(const float* in, int n_planes, int H, int W, double* out, unmore_stream_t stream);
+
+/* O(1) box sums from a table built over [n_img, planes_per_img, H, W]: the window is snapped
+ * like the crops (floor x1,y1 / ceil x2,y2, object_reasoning.py:502).  sums_out / means_out
+ * (nullable) [n_img, cap] fp64. */
+int unmore_box_sums(const double* sat, int n_img, int planes_per_img, int plane, int H, int W,
+                    const void* boxes, int boxes_f64, const int* counts, int cap, double* sums_out,
+                    double* means_out, unmore_stream_t stream);
+
+/* Bit-packing of dense masks: in [K, H, W] u8 (non-zero = set) -> out [K, H, ceil(W/32)] u32. */
+int unmore_mask_pack(const unsigned char* in, size_t K, int H, int W, uint32_t* out, unmore_stream_t stream);
+
+/* Area and tight box (half-open x1,y1,x2,y2; zeros if empty) of packed masks. */
+int unmore_mask_stats(const uint32_t* masks, int K, int H, int W, int* areas_out, int* tight_out,
+                      unmore_stream_t stream);
+
+/* Mask-IoU NMS on packed masks (north-star op (c); no reference counterpart, oracle = dense
+ * greedy restatement in torchvision's order): suppress j if popc(a&b)/(area_a+area_b-popc(a&b))
+ * > thr (fp32 division of exact integers).  areas / tight from unmore_mask_stats.
+ * order_ws [K] int32; matrix_ws [K * ceil(K/64)] u64; keep_out [K]; keep_count_out [1]. */
+int unmore_mask_nms(const uint32_t* masks, int K, int H, int W, const float* scores, const int* areas,
+                    const int* tight, float iou_threshold, int* order_ws, void* matrix_ws,
+                    int* keep_out, int* keep_count_out, unmore_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

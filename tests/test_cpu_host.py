@@ -1,0 +1,128 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares (no
+compute without a GPU), host logic of the mirrors, and the multi-rank gather on gloo."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "unmore_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(unmore_[a-z0-9_]+)\s*\(", src)) - {"unmore_stream_t"})
+
+
+def test_library_exports_every_declared_symbol():
+    from unmore_b200 import _lib
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/unmore_b200.h but not exported"
+    bound = set(_lib.SIGNATURES) | {"unmore_last_error", "unmore_version", "unmore_workspace_bytes"}
+    assert set(names) == bound, set(names) ^ bound
+    assert lib.unmore_version() >= 100
+    assert lib.unmore_workspace_bytes(10) >= 4 * 12
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a GPU tensor instead of routing to the oracle."""
+    from unmore_b200 import ops, _lib
+    with pytest.raises(_lib.UnmoreError):
+        ops.existence_scores(torch.zeros((1, 4, 8, 8)), torch.zeros((1, 1, 4)))
+    from unmore_b200.object_reasoning import Object_Discovery
+    with pytest.raises(RuntimeError):
+        Object_Discovery(device="cpu")
+    # nothing under unmore_b200/ imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "unmore_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_synth_is_deterministic_and_shaped():
+    from unmore_b200 import synth
+    a, b = synth.make_fields(17), synth.make_fields(17)
+    assert a.shape == (4, 480, 640) and a.dtype == torch.float32 and torch.equal(a, b)
+    assert not torch.equal(a, synth.make_fields(18))
+    nrm = torch.sqrt(a[1] ** 2 + a[2] ** 2)
+    inside = a[0] > 0
+    assert torch.allclose(nrm[inside], torch.ones_like(nrm[inside]), atol=1e-5) or inside.sum() == 0
+    assert float(nrm[~inside].max()) == 0.0
+    p = synth.make_proposals(17, 4096)
+    assert p.shape == (4096, 4) and p.dtype == np.float64
+    assert (p[:, 0] >= 0).all() and (p[:, 2] <= 640).all() and (p[:, 3] <= 480).all()
+    assert np.array_equal(p[:1225], synth.anchor_proposals(480, 640))
+
+
+def test_post_process_mirror():
+    from unmore_b200.post_process import select_annotations
+    anns = [dict(existence_score=0.6, center_score=0.9, boundary_score=0.8, area_score=0.5, score=0.1, bbox=[0, 0, 1, 1]),
+            dict(existence_score=0.4, center_score=0.9, boundary_score=0.8, area_score=0.6, score=0.2, bbox=[0, 0, 1, 1]),
+            dict(existence_score=0.5, center_score=0.8, boundary_score=0.75, area_score=0.7, score=0.3, bbox=[0, 0, 1, 1]),
+            dict(existence_score=0.9, center_score=0.79, boundary_score=0.9, area_score=0.8, score=0.4, bbox=[0, 0, 1, 1])]
+    sel = select_annotations(anns)
+    assert [a["id"] for a in sel] == [0, 1] and [a["score"] for a in sel] == [0.5, 0.7]  # thresholds are strict '<'
+
+
+def test_shard_ranges_cover_everything():
+    from unmore_b200.sharding import shard_indices, shard_range
+    for n, w in [(5000, 8), (7, 3), (2, 4), (0, 2)]:
+        got = sum((shard_indices(n, r, w) for r in range(w)), [])
+        assert got == list(range(n))
+        assert sorted(sum((shard_indices(n, r, w, interleave=True) for r in range(w)), [])) == list(range(n))
+        assert shard_range(n, w - 1, w)[1] == n
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from unmore_b200.sharding import shard_indices, pack_detections, gather_detections
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+n_images = 7
+def fake(i):   # deterministic ragged "detections" of image i
+    g = torch.Generator().manual_seed(i)
+    k = int(torch.randint(0, 5, (1,), generator=g))
+    return torch.rand((k, 4), generator=g), torch.rand((k,), generator=g)
+mine = shard_indices(n_images, rank, world, interleave=True)
+cap = 4
+boxes = torch.zeros((len(mine), cap, 4)); scores = torch.zeros((len(mine), cap)); counts = torch.zeros(len(mine), dtype=torch.int32)
+for j, i in enumerate(mine):
+    b, s = fake(i); boxes[j, :len(b)] = b; scores[j, :len(b)] = s; counts[j] = len(b)
+rows = pack_detections(torch.tensor(mine), boxes, counts, scores)
+allrows = gather_detections(rows)
+ref = []
+for i in range(n_images):
+    b, s = fake(i)
+    for k in range(len(b)):
+        ref.append(torch.cat([torch.tensor([float(i)]), b[k], s[k:k+1]]))
+ref = torch.stack(ref)
+assert allrows.shape == ref.shape and torch.equal(allrows, ref), (rank, allrows, ref)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_detections_world2_gloo(tmp_path):
+    """N>1 path on CPU: two gloo ranks, interleaved sharding, gathered result == single process."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs

@@ -1,0 +1,364 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden vectors
+and against the CPU oracle on seeded inputs.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): scores and box coordinates within 1e-5 relative in
+fp32 — for a coordinate the scale is max(|coordinate|, box side), because a round moves an
+edge by delta * side / 128 (object_reasoning.py:185-194); NMS keep-sets, labels, list
+membership / order and binary masks bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from unmore_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def od(dev):
+    from unmore_b200.object_reasoning import Object_Discovery
+    return Object_Discovery(device=dev)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from unmore_b200 import ops as _ops
+    return _ops
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def assert_boxes_close(got, ref, what=""):
+    got = np.asarray(got, np.float64).reshape(-1, 4)
+    ref = np.asarray(ref, np.float64).reshape(-1, 4)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if not len(ref):
+        return
+    side = np.maximum(ref[:, 2] - ref[:, 0], ref[:, 3] - ref[:, 1])[:, None]
+    scale = np.maximum(np.abs(ref), side)
+    err = np.abs(got - ref)
+    bad = err > RTOL * scale
+    assert not bad.any(), f"{what}: {int(bad.sum())} coords off, worst rel {np.max(err / np.maximum(scale, 1e-30)):.3e}"
+
+
+def assert_rel(got, ref, what="", rtol=RTOL):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = np.abs(got - ref)
+    assert (err <= rtol * np.abs(ref)).all(), f"{what}: worst rel {np.max(err / np.maximum(np.abs(ref), 1e-30)):.3e}"
+
+
+# ------------------------------------------------------------------------------------------
+# unit ops against reference goldens
+# ------------------------------------------------------------------------------------------
+def test_update_bbox_from_tiles(golden_dir, dev, ops):
+    g = _load(golden_dir, "units.npz")
+    d, mx = ops.update_bbox_from_tiles(torch.tensor(g["a10_tiles"], device=dev))
+    assert_rel(d.cpu().numpy(), g["a10_deltas"], "a10 deltas")
+    assert np.array_equal(mx.cpu().numpy(), g["a10_tiles"].max(axis=(1, 2)))
+
+
+def test_batch_erode_and_anti_center(golden_dir, dev, ops):
+    from unmore_b200.utils.misc import batch_erode
+    g = _load(golden_dir, "units.npz")
+    e = batch_erode(torch.tensor(g["a5_masks"], device=dev).long(), kernel_size=9, num_round=3)
+    assert e.dtype == torch.int64 and np.array_equal(e.cpu().numpy().astype(np.uint8), g["a5_out"])
+    a = ops.anti_center_map(torch.tensor(g["a6_in"], device=dev))
+    assert np.allclose(a.cpu().numpy(), g["a6_out"], rtol=0, atol=1e-14)
+
+
+def test_box_nms_golden(golden_dir, dev, ops):
+    g = _load(golden_dir, "units.npz")
+    b = torch.tensor(g["a14_boxes"], device=dev)[None].contiguous()
+    s = torch.tensor(g["a14_scores"], device=dev)[None].contiguous()
+    keep, kc, kb = ops.box_nms(b, s)
+    assert np.array_equal(keep[0, : int(kc[0])].cpu().numpy(), g["a14_keep"])
+    assert np.array_equal(kb[0, : int(kc[0])].cpu().numpy(), g["a14_boxes"][g["a14_keep"]])
+    keep, kc, _ = ops.box_nms(b, None)
+    assert np.array_equal(keep[0, : int(kc[0])].cpu().numpy(), g["a14_keep_allones"])
+    # matrix variant: same keep-set
+    assert np.array_equal(ops.box_nms_matrix(b[0], s[0]).cpu().numpy(), g["a14_keep"])
+    assert np.array_equal(ops.box_nms_matrix(b[0], None).cpu().numpy(), g["a14_keep_allones"])
+
+
+# ------------------------------------------------------------------------------------------
+# stage-by-stage against the reference's run on a synthetic scene (configs[0]: 512 proposals)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_scene_existence_and_center(golden_dir, od, dev, tag):
+    g = _load(golden_dir, f"scene_{tag}.npz")
+    idx, n_prop = int(g["index"]), int(g["n_prop"])
+    fields = synth.make_fields(idx).to(dev)
+    props = torch.tensor(synth.make_proposals(idx, n_prop))
+    ex = od.existence_checking(fields, props)["existence_scores"]
+    assert ex.dtype == torch.float32 and ex.device.type == "cpu"
+    assert_rel(ex.numpy(), g["existence_scores"], "existence")
+    assert np.array_equal(ex.numpy() >= 0.1, g["existence_scores"] >= 0.1)
+    p1 = props[torch.tensor(g["existence_scores"]) >= 0.1]
+    cr = od.center_reasoning(fields, p1)
+    assert cr["proposals_pass_singularity"].dtype == torch.float64
+    assert np.array_equal(cr["proposals_pass_singularity"].cpu().numpy(), g["pass1"])
+    assert np.array_equal(cr["splited_new_proposals"].cpu().numpy().reshape(-1, 4), g["split"].reshape(-1, 4))
+    if len(g["split"]):
+        sp = torch.tensor(g["split"])
+        ex2 = od.existence_checking(fields, sp)["existence_scores"].numpy()
+        assert_rel(ex2, g["split_existence"], "split existence")
+        cr2 = od.center_reasoning(fields, sp[torch.tensor(g["split_existence"]) >= 0.1])
+        assert np.array_equal(cr2["proposals_pass_singularity"].cpu().numpy(), g["pass2"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_scene_single_rounds_teacher_forced(golden_dir, od, dev, tag):
+    """optimize_one_image_single_round with inputs forced from the reference's own trajectory:
+    every recorded round, fp64 inputs on round 0 and fp32 afterwards."""
+    g = _load(golden_dir, f"scene_{tag}.npz")
+    fields = synth.make_fields(int(g["index"])).to(dev)
+    for r in range(int(g["n_trace"])):
+        pin = torch.tensor(g[f"r{r}_in"])
+        out = od.optimize_one_image_single_round(fields, pin)
+        assert np.array_equal(out["labels"].cpu().numpy(), g[f"r{r}_labels"]), f"labels, round {r}"
+        assert_boxes_close(out["updated_bboxes"].cpu().numpy(), g[f"r{r}_out"], f"round {r}")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_scene_full_trajectory_and_discovery(golden_dir, od, dev, tag):
+    g = _load(golden_dir, f"scene_{tag}.npz")
+    idx = int(g["index"])
+    fields = synth.make_fields(idx).to(dev)
+    br = od.boundary_reasoning(fields, torch.tensor(g["refine_in"]))
+    assert np.array_equal(br["labels"].cpu().numpy(), g["final_labels"])
+    assert_boxes_close(br["proposals"].cpu().numpy(), g["final_proposals"], "final proposals")
+    det = od.discover_image(fields, synth.make_proposals(idx, int(g["n_prop"])))
+    assert_boxes_close(det, g["discovered"], "discovered")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_scene_scoring(golden_dir, dev, tag):
+    from unmore_b200.object_scoring import Object_Scoring
+    g = _load(golden_dir, f"scene_{tag}.npz")
+    fields = synth.make_fields(int(g["index"])).to(dev)
+    sc = Object_Scoring(device=dev)
+    anns = sc.score_image(fields, g["discovered"].astype(np.float64).tolist(), image_id=int(g["index"]))
+    assert len(anns) == len(g["score_score"])
+    assert np.array_equal(np.array([a["bbox"] for a in anns], np.float32), g["score_bbox"])
+    for key in ("score", "existence_score", "center_score", "boundary_score", "area_score"):
+        assert_rel([a[key] for a in anns], g["score_" + key], key)
+    masks = np.stack([a["segmentation"]["mask"] for a in anns])
+    packed = np.packbits(masks.reshape(len(anns), -1), axis=1, bitorder="little")
+    assert np.array_equal(packed, g["score_masks_packed"]), "binary masks must be bit-exact"
+
+
+def test_main_loop_and_post_process(golden_dir, dev, od):
+    from unmore_b200.object_scoring import Object_Scoring
+    from unmore_b200.post_process import select_annotations
+    g = _load(golden_dir, "main_loop.npz")
+    H, W = int(g["H"]), int(g["W"])
+    ids = [int(i) for i in g["ids"]]
+    images = [synth.make_fields(i, H, W).to(dev) for i in ids]
+    res = od.main_object_discovery(images, ids)
+    for i in ids:
+        assert_boxes_close(res.get(i, np.zeros((0, 4))), g[f"disc_{i}"], f"image {i}")
+    raw = {str(i): g[f"disc_{i}"].astype(np.float64).tolist() for i in ids if len(g[f"disc_{i}"])}
+    anns = Object_Scoring(device=dev, raw_annotations=raw).main_object_scoring(images, ids)
+    assert np.array_equal(np.array([a["image_id"] for a in anns]), g["ann_image_id"])
+    assert np.array_equal(np.array([a["bbox"] for a in anns], np.float32).reshape(-1, 4), g["ann_bbox"])
+    for key in ("score", "existence_score", "center_score", "boundary_score", "area_score"):
+        assert_rel([a[key] for a in anns], g["ann_" + key], key)
+    sel = select_annotations(anns)
+    assert np.array_equal(np.array([a["id"] for a in sel]), g["pp_ids"])
+    assert np.array_equal(np.array([a["image_id"] for a in sel]), g["pp_image_id"])
+    assert_rel([a["score"] for a in sel], g["pp_score"], "post-process score")
+
+
+# ------------------------------------------------------------------------------------------
+# seeded inputs against the oracle (no golden): fractional boxes, edges, ragged batches
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [21, 22])
+def test_discovery_and_scoring_vs_oracle(dev, od, seed):
+    from unmore_b200.object_scoring import Object_Scoring
+    args = O.make_args()
+    img = synth.make_fields(seed)
+    props = synth.make_proposals(seed, 192)
+    dbg = {}
+    ref = O.discover_image(img, props, args, debug=dbg)
+    stats = {}
+    boxes = torch.tensor(props, device=dev)[None].contiguous()
+    kb, kc = od.discover_batch(img.to(dev)[None].contiguous(), boxes, stats=stats)
+    n_in = int(stats["refine_in"][0])
+    assert np.array_equal(stats["refine_in_boxes"][0, :n_in].cpu().numpy(), dbg["refine_in"].numpy())
+    assert_boxes_close(kb[0, : int(kc[0])].cpu().numpy(), ref, "discovered vs oracle")
+    if len(ref):
+        s_ref = O.score_image(img, ref.tolist(), args)
+        anns = Object_Scoring(device=dev).score_image(img.to(dev), ref.astype(np.float64).tolist())
+        assert np.array_equal(np.array([a["bbox"] for a in anns], np.float32), s_ref["bbox"])
+        assert_rel([a["score"] for a in anns], s_ref["score"], "score")
+        masks = np.stack([a["segmentation"]["mask"] for a in anns])
+        assert np.array_equal(masks, s_ref["masks"])
+
+
+def test_rasterise_both_resize_paths_vs_oracle(dev):
+    """Boxes chosen so that h+w <= 128 (ATen's small-output kernel) and > 128 (generic kernel),
+    dyadic sizes with exact 0.5 ties, image-edge boxes, one-pixel boxes."""
+    from unmore_b200.object_scoring import Object_Scoring
+    args = O.make_args()
+    img = synth.make_fields(31)
+    boxes = [[100, 100, 164, 164], [200, 50, 232, 82], [10.2, 20.7, 50.1, 70.9], [300, 200, 556, 456],
+             [0, 0, 640, 480], [600.5, 440.5, 640, 480], [320, 240, 321, 241], [50, 60, 114, 124],
+             [400, 100, 463.5, 163.5], [120, 300, 376, 364], [5, 5, 21, 117]]
+    s_ref = O.score_image(img, boxes, args)
+    sc = Object_Scoring(device=dev)
+    r = sc.score_batch(img.to(dev)[None].contiguous(), torch.tensor(boxes, dtype=torch.float64, device=dev)[None].contiguous())
+    n = int(r["keep_counts"][0])
+    keep = r["keep"][0, :n].cpu().numpy()
+    assert np.array_equal(keep, s_ref["nms_index"])
+    from unmore_b200.object_scoring import unpack_masks
+    dense = unpack_masks(r["masks"][0][torch.tensor(keep, device=dev).long()], 640)
+    assert np.array_equal(dense, s_ref["masks"])
+    assert np.array_equal(r["bbox"][0, :n].cpu().numpy(), s_ref["bbox"])
+    assert_rel(r["out"][0, :n, 0].cpu().numpy(), s_ref["score"], "score")
+
+
+def test_batch_equals_single_and_ragged(dev, od):
+    """Images are independent: a ragged batch must reproduce the per-image results exactly."""
+    ids = [3, 4, 5, 6]
+    n = [96, 0, 130, 61]
+    cap = max(n)
+    fields = torch.stack([synth.make_fields(i) for i in ids]).to(dev)
+    boxes = torch.zeros((len(ids), cap, 4), dtype=torch.float64)
+    for b, (i, k) in enumerate(zip(ids, n)):
+        if k:
+            boxes[b, :k] = torch.tensor(synth.make_proposals(i, 512)[100:100 + k])
+    counts = torch.tensor(n, dtype=torch.int32, device=dev)
+    kb, kc = od.discover_batch(fields, boxes.to(dev), counts)
+    assert int(kc[1]) == 0
+    for b, (i, k) in enumerate(zip(ids, n)):
+        single = od.discover_image(fields[b], boxes[b, :k]) if k else np.zeros((0, 4), np.float32)
+        assert np.array_equal(kb[b, : int(kc[b])].cpu().numpy(), single)
+
+
+def test_empty_and_degenerate_inputs(dev, od, ops):
+    fields = synth.make_fields(2).to(dev)
+    assert od.existence_checking(fields, np.zeros((0, 4)))["existence_scores"].shape == (0,)
+    cr = od.center_reasoning(fields, np.zeros((0, 4)))
+    assert cr["proposals_pass_singularity"].shape == (0, 4) and cr["splited_new_proposals"].shape == (0, 4)
+    assert od.boundary_reasoning(fields, np.zeros((0, 4))) == {"proposals": [], "labels": []}
+    # boxes below the area threshold are filtered before round 0 (object_reasoning.py:293-299, strict >)
+    small = torch.tensor([[10, 10, 20, 15], [10, 10, 20, 15.0001], [5, 5, 5, 80]], dtype=torch.float64)
+    out, lab, rounds = ops.boundary_refine(fields[None].contiguous(), small.to(dev)[None].contiguous())
+    assert lab[0, 0].item() == -2 and lab[0, 2].item() == -2
+    assert rounds[0].tolist()[0] == 0 and rounds[0].tolist()[2] == 0 and rounds[0].tolist()[1] >= 1
+    # NMS of nothing
+    keep, kc, _ = ops.box_nms(torch.zeros((2, 0, 4), device=dev), None)
+    assert kc.tolist() == [0, 0]
+
+
+def test_error_reporting(dev, ops):
+    from unmore_b200._lib import UnmoreError
+    with pytest.raises(UnmoreError):
+        ops.existence_scores(torch.zeros((1, 4, 8, 8)), torch.zeros((1, 1, 4), device=dev))  # CPU fields: no fallback
+    with pytest.raises(UnmoreError):
+        ops.box_nms(torch.zeros((1, 40000, 4), device=dev))  # capacity limit reported, not truncated
+
+
+# ------------------------------------------------------------------------------------------
+# north-star-only ops (parity unpinned by the reference: definitional oracles)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 480, 640), (2, 37, 53), (1, 128, 1024), (5, 64, 130)])
+def test_sat_and_box_sums(dev, ops, shape):
+    g = torch.Generator().manual_seed(7)
+    f = torch.rand(shape, generator=g)
+    ref = O.sat_build(f)
+    got = ops.sat_build(f.to(dev)).cpu()
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, rtol=1e-12, atol=1e-9)
+    H, W = shape[1:]
+    boxes = torch.rand((shape[0], 50, 4), generator=g, dtype=torch.float64)
+    boxes[..., 0] *= W / 2; boxes[..., 1] *= H / 2
+    boxes[..., 2] = boxes[..., 0] + boxes[..., 2] * W / 2; boxes[..., 3] = boxes[..., 1] + boxes[..., 3] * H / 2
+    sums, means = ops.box_sums(got.to(dev)[:, None].contiguous(), 0, boxes.to(dev))
+    for b in range(shape[0]):
+        r = O.box_sums(ref[b], boxes[b])
+        assert torch.allclose(sums[b].cpu(), r, rtol=1e-12, atol=1e-9)
+        # against the definition, 1e-5 relative (what an fp32 table could not deliver)
+        x1, y1, x2, y2 = O.snap_box(boxes[b, 0])
+        assert abs(sums[b, 0].item() - f[b, y1:y2, x1:x2].double().sum().item()) <= 1e-9 * max(1.0, r[0].item())
+
+
+def _random_masks(k, H, W, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.zeros((k, H, W), dtype=np.uint8)
+    for i in range(k):
+        cy, cx = rng.uniform(0, H), rng.uniform(0, W)
+        ry, rx = rng.uniform(8, H / 3), rng.uniform(8, W / 3)
+        m[i] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) < 1
+    m[k // 2] = m[k // 3]          # exact duplicate
+    m[k - 1] = 0                   # empty mask
+    return m
+
+
+@pytest.mark.parametrize("W", [640, 100])
+def test_mask_pack_and_mask_nms(dev, ops, W):
+    H, k = 120, 150
+    dense = _random_masks(k, H, W, seed=5)
+    packed = ops.mask_pack(torch.tensor(dense, device=dev))
+    ref_packed = np.packbits(np.pad(dense, ((0, 0), (0, 0), (0, (-W) % 32))), axis=2, bitorder="little").view(np.uint32)
+    assert np.array_equal(packed.cpu().numpy().view(np.uint32), ref_packed.reshape(k, H, -1))
+    areas, tight = ops.mask_stats(packed, W)
+    assert np.array_equal(areas.cpu().numpy(), dense.reshape(k, -1).sum(1))
+    rng = np.random.default_rng(1)
+    scores = rng.random(k).astype(np.float32)
+    scores[10:40] = 0.5            # ties: index order decides
+    keep = ops.mask_nms(packed, W, torch.tensor(scores, device=dev), 0.5).cpu().numpy()
+    assert np.array_equal(keep, O.mask_nms_dense(dense, scores, 0.5))
+    keep = ops.mask_nms(packed, W, torch.tensor(scores, device=dev), 0.1).cpu().numpy()
+    assert np.array_equal(keep, O.mask_nms_dense(dense, scores, 0.1))
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (configs[1] shapes: 480x640 fields, 4096 proposals per image)
+# ------------------------------------------------------------------------------------------
+def test_full_size_properties(dev, od, ops):
+    B, N = 6, 4096
+    fields = torch.stack([synth.make_fields(100 + i) for i in range(B)]).to(dev)
+    props = torch.tensor(np.stack([synth.make_proposals(100 + i, N) for i in range(B)])).to(dev)
+    st = {}
+    kb, kc = od.discover_batch(fields, props, stats=st)
+    kb2, kc2 = od.discover_batch(fields, props)
+    assert torch.equal(kc, kc2) and torch.equal(kb, kb2), "run-to-run determinism"
+    assert int(kc.min()) > 0
+    # 1. every label-1 box is a fixed point of one more round (idempotence of the converged set)
+    lab = st["refine_labels"]
+    rb = st["refine_boxes"]
+    for b in range(B):
+        n = int(st["refine_in"][b])
+        ok = lab[b, :n] == 1
+        conv = rb[b, :n][ok].contiguous()
+        out, l2, _ = ops.boundary_refine(fields[b:b + 1], conv[None].contiguous(), n_round=1, apply_small_filter=False,
+                                         early_exit=False)
+        assert bool((l2[0] == 1).all()) and torch.equal(out[0], conv)
+    # 2. NMS invariants on the label-1 set, in index order (all scores equal)
+    for b in range(B):
+        n = int(st["label1"][b])
+        fin, _, _ = ops.compact_boxes(rb[b:b + 1], st["refine_in"][b:b + 1], ops.MODE_LABEL_EQ, lab[b:b + 1], thr=1.0,
+                                      out_dtype=torch.float32)
+        cand = fin[0, :n].cpu().numpy()
+        ref_keep = O.nms(cand, np.ones(n, np.float32), 0.5)
+        assert np.array_equal(kb[b, : int(kc[b])].cpu().numpy(), cand[ref_keep])
+    # 3. existence scores are means of values in (0,1); lists only shrink where they must
+    ex = st["existence_scores"]
+    assert bool(((ex >= 0) & (ex <= 1)).all())
+    assert bool((st["pass1"] <= N).all()) and bool((st["refine_in"] <= 5 * N).all())

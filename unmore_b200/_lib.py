@@ -24,6 +24,16 @@ SIGNATURES = {
     "unmore_update_bbox_from_tiles": [_p, _i, _p, _p, _p],
     "unmore_compact_boxes": [_p, _i, _p, _i, _i, _i, _p, _f, _p, _i, _i, _p, _i, _p, _i, _p],
     "unmore_box_nms": [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p],
+    "unmore_batch_erode": [_p, _i, _i, _i, _i, _i, _p, _p],
+    "unmore_anti_center_map": [_p, _i, _i, _i, _i, _p, _p],
+    "unmore_box_nms_matrix": [_p, _p, _i, _f, _p, _p, _p, _p, _p],
+    "unmore_score_and_rasterise": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
+    "unmore_final_scores": [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p],
+    "unmore_sat_build": [_p, _i, _i, _i, _p, _p],
+    "unmore_box_sums": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
+    "unmore_mask_pack": [_p, C.c_size_t, _i, _i, _p, _p],
+    "unmore_mask_stats": [_p, _i, _i, _i, _p, _p, _p],
+    "unmore_mask_nms": [_p, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p],
 }
 
 _lib = None

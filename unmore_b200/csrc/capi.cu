@@ -60,6 +60,17 @@ int make_worklist(WorkList& w, const int* counts, int n_img, int cap, void* ws, 
   return 0;
 }
 
+// F.normalize(filter, dim=1) in fp32 then .double() (object_reasoning.py:372-373):
+// filt[i*5+j] = (2-i)/max(sqrt((2-i)^2+(2-j)^2), 1e-12); channel 1 reads the transposed entry
+void anti_center_filter(double* filt) {
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) {
+      const int di = 2 - i, dj = 2 - j;
+      const float n = std::sqrt((float)(di * di + dj * dj));
+      filt[i * 5 + j] = (double)((float)di / (n > 1e-12f ? n : 1e-12f));
+    }
+}
+
 int check_fields(const float* f, int n_img, int C, int H, int W) {
   if (!f || n_img <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UNMORE_E_INVALID, "bad field tensor");
   return 0;
@@ -103,13 +114,7 @@ int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W,
   p.ch_sdf = ch_sdf; p.ch_crow = ch_center_row; p.ch_ccol = ch_center_col;
   p.boxes = boxes; p.boxes_f64 = boxes_f64; p.thr = center_score_max_thres;
   p.max_values = max_values_out; p.argmax = argmax_out; p.splits = splits_out;
-  for (int i = 0; i < 5; ++i)
-    for (int j = 0; j < 5; ++j) {
-      const int di = 2 - i, dj = 2 - j;
-      // F.normalize(dim=1): v / max(||v||_2, 1e-12), fp32; the centre tap is 0 / 1e-12 = 0
-      const float n = std::sqrt((float)(di * di + dj * dj));
-      p.filt[i * 5 + j] = (double)((float)di / (n > 1e-12f ? n : 1e-12f));
-    }
+  anti_center_filter(p.filt);
   if (int e = make_worklist(p.work, counts, n_img, cap, ws, s)) return e;
   return cuda_fail(launch_center(p, num_sms(), s), "center_kernel");
 }
@@ -164,6 +169,108 @@ int unmore_box_nms(const float* boxes, const float* scores, const int* counts, i
   p.iou_thr = iou_threshold; p.keep = keep_out; p.keep_counts = keep_counts_out;
   p.boxes_out = reinterpret_cast<float4*>(boxes_out); p.order_ws = order_ws; p.alive_ws = nullptr;
   return cuda_fail(launch_box_nms(p, (cudaStream_t)stream), "box_nms_kernel");
+}
+
+int unmore_batch_erode(const unsigned char* masks, int B, int H, int W, int kernel_size, int num_round,
+                       unsigned char* out, unmore_stream_t stream) {
+  if (B < 0 || kernel_size < 1 || !(kernel_size & 1) || num_round < 0 || (B > 0 && (!masks || !out)))
+    return fail(UNMORE_E_INVALID, "unmore_batch_erode: bad argument");
+  if (H != kCrop || W != kCrop) return fail(UNMORE_E_CAPACITY, "unmore_batch_erode: only 128x128 crops (got %dx%d)", H, W);
+  return cuda_fail(launch_erode(masks, out, B, kernel_size, num_round, (cudaStream_t)stream), "erode_kernel");
+}
+
+int unmore_anti_center_map(const float* vote_maps, int B, int H, int W, int kernel_size, double* out,
+                           unmore_stream_t stream) {
+  if (B < 0 || H <= 0 || W <= 0 || (B > 0 && (!vote_maps || !out)))
+    return fail(UNMORE_E_INVALID, "unmore_anti_center_map: bad argument");
+  if (kernel_size != 5) return fail(UNMORE_E_CAPACITY, "unmore_anti_center_map: kernel_size must be 5 (reference call site)");
+  double filt[25];
+  anti_center_filter(filt);
+  return cuda_fail(launch_anti_center(vote_maps, out, B, H, W, filt, (cudaStream_t)stream), "anti_center_kernel");
+}
+
+int unmore_box_nms_matrix(const float* boxes, const float* scores, int K, float iou_threshold, int* order_ws,
+                          void* matrix_ws, int* keep_out, int* keep_count_out, unmore_stream_t stream) {
+  if (K < 0 || !keep_count_out || (K > 0 && (!boxes || !order_ws || !matrix_ws || !keep_out)))
+    return fail(UNMORE_E_INVALID, "unmore_box_nms_matrix: bad argument");
+  return cuda_fail(launch_matrix_nms(nullptr, reinterpret_cast<const float4*>(boxes), K, 0, 0, scores, nullptr, nullptr,
+                                     iou_threshold, order_ws, reinterpret_cast<unsigned long long*>(matrix_ws), keep_out,
+                                     keep_count_out, (cudaStream_t)stream),
+                   "box matrix nms");
+}
+
+int unmore_score_and_rasterise(const float* fields, int n_img, int C, int H, int W, int ch_sdf, int ch_center_row,
+                               int ch_center_col, int ch_exist, const void* boxes, int boxes_f64, const int* counts,
+                               int cap, float* scores_out, float* tight_out, int* areas_out, uint32_t* masks_out,
+                               unmore_stream_t stream) {
+  if (int e = check_fields(fields, n_img, C, H, W)) return e;
+  if (!boxes || !scores_out || !tight_out || !areas_out || cap < 0 || ch_sdf < 0 || ch_sdf >= C || ch_center_row < 0 ||
+      ch_center_row >= C || ch_center_col < 0 || ch_center_col >= C || ch_exist < 0 || ch_exist >= C)
+    return fail(UNMORE_E_INVALID, "unmore_score_and_rasterise: bad argument");
+  if (n_img > 65535) return fail(UNMORE_E_CAPACITY, "unmore_score_and_rasterise: n_img > 65535 per call");
+  ScoreParams p{};
+  p.fields = fields; p.n_img = n_img; p.C = C; p.H = H; p.W = W;
+  p.ch_sdf = ch_sdf; p.ch_crow = ch_center_row; p.ch_ccol = ch_center_col; p.ch_exist = ch_exist;
+  p.boxes = boxes; p.boxes_f64 = boxes_f64; p.counts = counts; p.cap = cap;
+  p.scores = reinterpret_cast<float4*>(scores_out); p.tight = reinterpret_cast<float4*>(tight_out);
+  p.areas = areas_out; p.masks = masks_out;
+  return cuda_fail(launch_score(p, (cudaStream_t)stream), "score_kernel");
+}
+
+int unmore_final_scores(const float* scores, const float* tight, const int* areas, const int* keep,
+                        const int* keep_counts, int cap, int n_img, float existence_score_thres, float center_score_thres,
+                        float boundary_score_thres, double* out, float* bbox_xywh_out, unsigned char* selected_out,
+                        unmore_stream_t stream) {
+  if (!scores || !tight || !areas || !keep || !keep_counts || !out || !bbox_xywh_out || cap < 0 || n_img < 0)
+    return fail(UNMORE_E_INVALID, "unmore_final_scores: bad argument");
+  FinalParams p{};
+  p.scores = reinterpret_cast<const float4*>(scores); p.tight = reinterpret_cast<const float4*>(tight);
+  p.areas = areas; p.keep = keep; p.keep_counts = keep_counts; p.cap = cap; p.n_img = n_img;
+  p.existence_thres = existence_score_thres; p.center_thres = center_score_thres; p.boundary_thres = boundary_score_thres;
+  p.out = out; p.bbox_xywh = reinterpret_cast<float4*>(bbox_xywh_out); p.selected = selected_out;
+  return cuda_fail(launch_final_scores(p, (cudaStream_t)stream), "final_scores_kernel");
+}
+
+int unmore_sat_build(const float* in, int n_planes, int H, int W, double* out, unmore_stream_t stream) {
+  if (n_planes < 0 || H <= 0 || W <= 0 || (n_planes > 0 && (!in || !out)))
+    return fail(UNMORE_E_INVALID, "unmore_sat_build: bad argument");
+  if (W > 2048) return fail(UNMORE_E_CAPACITY, "unmore_sat_build: W %d > 2048", W);
+  return cuda_fail(launch_sat(in, out, n_planes, H, W, (cudaStream_t)stream), "sat_kernel");
+}
+
+int unmore_box_sums(const double* sat, int n_img, int planes_per_img, int plane, int H, int W, const void* boxes,
+                    int boxes_f64, const int* counts, int cap, double* sums_out, double* means_out,
+                    unmore_stream_t stream) {
+  if (!sat || !boxes || !sums_out || n_img < 0 || cap < 0 || plane < 0 || plane >= planes_per_img)
+    return fail(UNMORE_E_INVALID, "unmore_box_sums: bad argument");
+  return cuda_fail(launch_box_sums(sat, planes_per_img, plane, H, W, boxes, boxes_f64, counts, cap, n_img, sums_out,
+                                   means_out, (cudaStream_t)stream),
+                   "box_sums_kernel");
+}
+
+int unmore_mask_pack(const unsigned char* in, size_t K, int H, int W, uint32_t* out, unmore_stream_t stream) {
+  if (H <= 0 || W <= 0 || (K > 0 && (!in || !out))) return fail(UNMORE_E_INVALID, "unmore_mask_pack: bad argument");
+  return cuda_fail(launch_mask_pack(in, out, K, H, W, (cudaStream_t)stream), "pack_kernel");
+}
+
+int unmore_mask_stats(const uint32_t* masks, int K, int H, int W, int* areas_out, int* tight_out,
+                      unmore_stream_t stream) {
+  if (K < 0 || H <= 0 || W <= 0 || (K > 0 && (!masks || !areas_out || !tight_out)))
+    return fail(UNMORE_E_INVALID, "unmore_mask_stats: bad argument");
+  return cuda_fail(launch_mask_stats(masks, K, H, (W + 31) >> 5, areas_out, reinterpret_cast<int4*>(tight_out),
+                                     (cudaStream_t)stream),
+                   "mask_stats_kernel");
+}
+
+int unmore_mask_nms(const uint32_t* masks, int K, int H, int W, const float* scores, const int* areas, const int* tight,
+                    float iou_threshold, int* order_ws, void* matrix_ws, int* keep_out, int* keep_count_out,
+                    unmore_stream_t stream) {
+  if (K < 0 || !keep_count_out || (K > 0 && (!masks || !areas || !tight || !order_ws || !matrix_ws || !keep_out)))
+    return fail(UNMORE_E_INVALID, "unmore_mask_nms: bad argument");
+  return cuda_fail(launch_matrix_nms(masks, nullptr, K, H, (W + 31) >> 5, scores, areas, reinterpret_cast<const int4*>(tight),
+                                     iou_threshold, order_ws, reinterpret_cast<unsigned long long*>(matrix_ws), keep_out,
+                                     keep_count_out, (cudaStream_t)stream),
+                   "mask matrix nms");
 }
 
 }  // extern "C"

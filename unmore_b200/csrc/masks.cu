@@ -1,0 +1,222 @@
+// Bit-packed masks and mask-IoU NMS (north-star op (c); no reference counterpart — SURVEY.md
+// §8a row C — the oracle is a dense greedy restatement with the order / tie-break of
+// torchvision.ops.nms).
+//
+//   pack:   dense u8 [K, H, W] (non-zero = set) -> u32 [K, H, ceil(W/32)], LSB = lowest x
+//   stats:  area (popcount) and tight box of every packed mask
+//   nms:    stable descending rank sort -> 64-wide suppression bit-matrix with exact integer
+//           IoU (popc(a & b) over the intersection of the tight boxes only, skipped when the
+//           box-overlap / area bound already proves IoU <= thr) -> single-warp greedy scan
+#include "unmore_internal.h"
+
+namespace unmore {
+
+// ---- pack --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nz4(uint32_t w) {  // 4 bytes -> 4 bits (byte != 0)
+  const uint32_t m = __vcmpne4(w, 0u);                 // 0xFF per non-zero byte
+  return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+}
+
+// fast path: W % 32 == 0.  Lane loads 16 pixels (one uint4), pairs of lanes form a word.
+__global__ void __launch_bounds__(256) pack_kernel_vec(const uint4* __restrict__ in, uint32_t* __restrict__ out,
+                                                       size_t n_vec) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bits = 0;
+  if (i < n_vec) {
+    const uint4 v = __ldcs(in + i);
+    bits = nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
+  }
+  const uint32_t hi = __shfl_down_sync(kFullMask, bits, 1);
+  if (!(threadIdx.x & 1) && i < n_vec) __stcs(out + (i >> 1), bits | (hi << 16));
+}
+
+__global__ void __launch_bounds__(256) pack_kernel_generic(const unsigned char* __restrict__ in,
+                                                           uint32_t* __restrict__ out, size_t n_rows, int W, int Wp) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_rows * Wp) return;
+  const size_t r = q / Wp;
+  const int wx = (int)(q - r * Wp);
+  const unsigned char* p = in + r * W + (size_t)wx * 32;
+  const int n = min(32, W - wx * 32);
+  uint32_t word = 0;
+  for (int b = 0; b < n; ++b) word |= (p[b] ? 1u : 0u) << b;
+  out[q] = word;
+}
+
+int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, cudaStream_t stream) {
+  if (n_masks == 0) return 0;
+  const int Wp = (W + 31) >> 5;
+  if ((W & 31) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const size_t n_vec = n_masks * H * (size_t)W / 16;
+    pack_kernel_vec<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), out, n_vec);
+  } else {
+    const size_t total = n_masks * H * (size_t)Wp;
+    pack_kernel_generic<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, n_masks * (size_t)H, W, Wp);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- stats -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_stats_kernel(const uint32_t* __restrict__ masks, int K, int H, int Wp,
+                                                         int* __restrict__ areas, int4* __restrict__ tight) {
+  __shared__ int s_area, s_x1, s_y1, s_x2, s_y2;
+  const int k = blockIdx.x;
+  if (threadIdx.x == 0) { s_area = 0; s_x1 = 1 << 30; s_y1 = 1 << 30; s_x2 = -1; s_y2 = -1; }
+  __syncthreads();
+  const uint32_t* m = masks + (size_t)k * H * Wp;
+  int area = 0, x1 = 1 << 30, y1 = 1 << 30, x2 = -1, y2 = -1;
+  for (int q = threadIdx.x; q < H * Wp; q += blockDim.x) {
+    const uint32_t w = __ldg(m + q);
+    if (w) {
+      const int y = q / Wp, xb = (q - y * Wp) << 5;
+      area += __popc(w);
+      x1 = min(x1, xb + __ffs(w) - 1); x2 = max(x2, xb + 31 - __clz(w));
+      y1 = min(y1, y); y2 = max(y2, y);
+    }
+  }
+  area = warp_sum(area);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x1 = min(x1, __shfl_xor_sync(kFullMask, x1, o)); y1 = min(y1, __shfl_xor_sync(kFullMask, y1, o));
+    x2 = max(x2, __shfl_xor_sync(kFullMask, x2, o)); y2 = max(y2, __shfl_xor_sync(kFullMask, y2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_area, area);
+    atomicMin(&s_x1, x1); atomicMin(&s_y1, y1); atomicMax(&s_x2, x2); atomicMax(&s_y2, y2);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    areas[k] = s_area;
+    tight[k] = s_area > 0 ? make_int4(s_x1, s_y1, s_x2 + 1, s_y2 + 1) : make_int4(0, 0, 0, 0);  // half-open
+  }
+}
+
+// ---- stable descending rank sort ---------------------------------------------------------
+__global__ void __launch_bounds__(256) rank_sort_kernel(const float* __restrict__ scores, int K, int* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  if (!scores) { order[i] = i; return; }
+  const float si = scores[i];
+  int rank = 0;
+  for (int j = 0; j < K; ++j) {
+    const float sj = __ldg(scores + j);
+    rank += (sj > si || (sj == si && j < i)) ? 1 : 0;
+  }
+  order[rank] = i;
+}
+
+// ---- suppression bit-matrix --------------------------------------------------------------
+// grid (cb, rb) with cb >= rb; thread t of the CTA owns sorted row rb*64+t against the 64 sorted
+// columns of block cb.  matrix[r][cb] bit c  <=>  IoU(sorted r, sorted cb*64+c) > thr, c later than r.
+__global__ void __launch_bounds__(64) mask_iou_matrix_kernel(const uint32_t* __restrict__ masks, int K, int H, int Wp,
+                                                             const int* __restrict__ order, const int* __restrict__ areas,
+                                                             const int4* __restrict__ tight, float thr,
+                                                             unsigned long long* __restrict__ matrix) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ int s_idx[64], s_area[64];
+  __shared__ int4 s_box[64];
+  const int cols = min(64, K - cb * 64);
+  if ((int)threadIdx.x < cols) {
+    const int j = order[cb * 64 + threadIdx.x];
+    s_idx[threadIdx.x] = j; s_area[threadIdx.x] = areas[j]; s_box[threadIdx.x] = tight[j];
+  }
+  __syncthreads();
+  const int r = rb * 64 + threadIdx.x;
+  if (r >= K) return;
+  const int i = order[r];
+  const int ai = areas[i];
+  const int4 bi = tight[i];
+  const uint32_t* mi = masks + (size_t)i * H * Wp;
+  const int nblk = (K + 63) >> 6;
+  unsigned long long bits = 0ull;
+  const int c0 = (rb == cb) ? (int)threadIdx.x + 1 : 0;
+  for (int c = c0; c < cols; ++c) {
+    const int4 bj = s_box[c];
+    const int ix1 = max(bi.x, bj.x), iy1 = max(bi.y, bj.y), ix2 = min(bi.z, bj.z), iy2 = min(bi.w, bj.w);
+    if (ix2 <= ix1 || iy2 <= iy1) continue;
+    const int aj = s_area[c];
+    const int ub = min(min(ai, aj), (ix2 - ix1) * (iy2 - iy1));
+    if (!(__fdiv_rn((float)ub, (float)(ai + aj - ub)) > thr)) continue;  // IoU is monotone in the intersection
+    const uint32_t* mj = masks + (size_t)s_idx[c] * H * Wp;
+    const int w1 = ix1 >> 5, w2 = (ix2 + 31) >> 5;
+    int inter = 0;
+    for (int y = iy1; y < iy2; ++y) {
+      const uint32_t* pi = mi + (size_t)y * Wp;
+      const uint32_t* pj = mj + (size_t)y * Wp;
+      for (int w = w1; w < w2; ++w) inter += __popc(__ldg(pi + w) & __ldg(pj + w));
+    }
+    if (__fdiv_rn((float)inter, (float)(ai + aj - inter)) > thr) bits |= 1ull << c;
+  }
+  matrix[(size_t)r * nblk + cb] = bits;
+}
+
+// Box-IoU variant of the matrix (torchvision arithmetic), for large-K box NMS.
+__global__ void __launch_bounds__(64) box_iou_matrix_kernel(const float4* __restrict__ boxes, int K,
+                                                            const int* __restrict__ order, float thr,
+                                                            unsigned long long* __restrict__ matrix) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ float4 s_box[64];
+  const int cols = min(64, K - cb * 64);
+  if ((int)threadIdx.x < cols) s_box[threadIdx.x] = boxes[order[cb * 64 + threadIdx.x]];
+  __syncthreads();
+  const int r = rb * 64 + threadIdx.x;
+  if (r >= K) return;
+  const float4 bi = boxes[order[r]];
+  const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+  const int nblk = (K + 63) >> 6;
+  unsigned long long bits = 0ull;
+  const int c0 = (rb == cb) ? (int)threadIdx.x + 1 : 0;
+  for (int c = c0; c < cols; ++c) {
+    const float4 bj = s_box[c];
+    const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y), xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+    if (__fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter)) > thr) bits |= 1ull << c;
+  }
+  matrix[(size_t)r * nblk + cb] = bits;
+}
+
+// ---- greedy scan over the matrix (one warp) -----------------------------------------------
+__global__ void __launch_bounds__(32) greedy_scan_kernel(const unsigned long long* __restrict__ matrix, int K,
+                                                         const int* __restrict__ order, int* __restrict__ keep,
+                                                         int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long removed[];  // ceil(K/64) words
+  const int nblk = (K + 63) >> 6;
+  const int lane = threadIdx.x;
+  for (int w = lane; w < nblk; w += 32) removed[w] = 0ull;
+  __syncwarp();
+  int nk = 0;
+  for (int i = 0; i < K; ++i) {
+    if ((removed[i >> 6] >> (i & 63)) & 1ull) continue;  // uniform
+    if (lane == 0) keep[nk] = order[i];
+    ++nk;
+    const unsigned long long* row = matrix + (size_t)i * nblk;
+    for (int w = (i >> 6) + lane; w < nblk; w += 32) removed[w] |= row[w];
+    __syncwarp();
+  }
+  if (lane == 0) *keep_count = nk;
+}
+
+int launch_mask_stats(const uint32_t* masks, int K, int H, int Wp, int* areas, int4* tight, cudaStream_t stream) {
+  if (K <= 0) return 0;
+  mask_stats_kernel<<<K, 256, 0, stream>>>(masks, K, H, Wp, areas, tight);
+  return (int)cudaGetLastError();
+}
+
+int launch_matrix_nms(const uint32_t* masks, const float4* boxes, int K, int H, int Wp, const float* scores,
+                      const int* areas, const int4* tight, float thr, int* order, unsigned long long* matrix,
+                      int* keep, int* keep_count, cudaStream_t stream) {
+  if (K <= 0) return (int)cudaMemsetAsync(keep_count, 0, sizeof(int), stream);
+  rank_sort_kernel<<<(K + 255) / 256, 256, 0, stream>>>(scores, K, order);
+  const int nblk = (K + 63) >> 6;
+  dim3 grid(nblk, nblk);
+  if (masks) mask_iou_matrix_kernel<<<grid, 64, 0, stream>>>(masks, K, H, Wp, order, areas, tight, thr, matrix);
+  else box_iou_matrix_kernel<<<grid, 64, 0, stream>>>(boxes, K, order, thr, matrix);
+  greedy_scan_kernel<<<1, 32, nblk * sizeof(unsigned long long), stream>>>(matrix, K, order, keep, keep_count);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace unmore

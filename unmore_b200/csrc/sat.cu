@@ -1,0 +1,121 @@
+// Summed-area tables of per-image fields and O(1) box sums (north-star op (a); the reference
+// has no counterpart — SURVEY.md §8a row A — so the oracle is a float64 cumsum restatement).
+//
+//   S[y][x] = sum_{v<y, u<x} f[v][u]   stored as fp64 [H+1, W+1] (first row / column zero)
+//   boxsum  = S[y2][x2] - S[y1][x2] - S[y2][x1] + S[y1][x1]   on the snapped window
+//
+// fp64 because an fp32 table of a 480x640 field reaches ~3e5 and differencing then loses
+// ~2e-2 absolute.  HBM-bound: 4 B read + 8 B written per pixel.  One warp sweeps one plane top
+// to bottom: each lane owns 4 consecutive columns of every 128-column step (one coalesced
+// float4 load), does a 3-add serial prefix, a 5-step warp-shuffle scan of the lane totals,
+// and keeps the running column sums (the vertical scan) in registers, so no shared-memory
+// exchange or barrier is needed.  Results are restaged through a 1 KB per-warp shared buffer
+// so every global store instruction writes 32 consecutive doubles.
+#include "unmore_internal.h"
+
+namespace unmore {
+
+constexpr int kSatWarps = 4;
+
+__device__ __forceinline__ double shfl_up_d(double v, int o) { return __shfl_up_sync(kFullMask, v, o); }
+
+template <int STEPS>
+__global__ void __launch_bounds__(kSatWarps * 32) sat_kernel(const float* __restrict__ in, double* __restrict__ out,
+                                                              int n_planes, int H, int W) {
+  __shared__ double stage[kSatWarps][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int plane = blockIdx.x * kSatWarps + warp;
+  if (plane >= n_planes) return;
+  const float* src = in + (size_t)plane * H * W;
+  double* dst = out + (size_t)plane * (H + 1) * (W + 1);
+  const int OW = W + 1;
+  for (int x = lane; x < OW; x += 32) dst[x] = 0.0;  // row 0
+  double vacc[STEPS][4];
+#pragma unroll
+  for (int s = 0; s < STEPS; ++s) vacc[s][0] = vacc[s][1] = vacc[s][2] = vacc[s][3] = 0.0;
+  const bool vec_ok = (W & 3) == 0;
+  for (int y = 0; y < H; ++y) {
+    const float* rowp = src + (size_t)y * W;
+    double* orow = dst + (size_t)(y + 1) * OW;
+    float4 v[STEPS];
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      const int x = s * 128 + 4 * lane;
+      if (vec_ok && x + 3 < W) {
+        v[s] = __ldcs(reinterpret_cast<const float4*>(rowp + x));  // streamed once: evict-first
+      } else {
+        v[s].x = x < W ? rowp[x] : 0.f;
+        v[s].y = x + 1 < W ? rowp[x + 1] : 0.f;
+        v[s].z = x + 2 < W ? rowp[x + 2] : 0.f;
+        v[s].w = x + 3 < W ? rowp[x + 3] : 0.f;
+      }
+    }
+    if (lane == 0) orow[0] = 0.0;  // column 0
+    double carry = 0.0;            // row prefix of everything left of this step
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+      if (s * 128 >= W) break;
+      const double a0 = (double)v[s].x, a1 = a0 + (double)v[s].y, a2 = a1 + (double)v[s].z, a3 = a2 + (double)v[s].w;
+      double incl = a3;  // inclusive scan of lane totals
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = shfl_up_d(incl, o);
+        if (lane >= o) incl += t;
+      }
+      const double base = carry + (incl - a3);
+      carry += __shfl_sync(kFullMask, incl, 31);
+      vacc[s][0] += base + a0; vacc[s][1] += base + a1; vacc[s][2] += base + a2; vacc[s][3] += base + a3;
+      // restage: lane l holds columns 4l..4l+3; store instruction j writes columns 32j + lane
+      __syncwarp();
+      *reinterpret_cast<double2*>(&stage[warp][4 * lane]) = make_double2(vacc[s][0], vacc[s][1]);
+      *reinterpret_cast<double2*>(&stage[warp][4 * lane + 2]) = make_double2(vacc[s][2], vacc[s][3]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = s * 128 + 32 * j + lane;
+        if (x < W) __stcs(orow + 1 + x, stage[warp][32 * j + lane]);
+      }
+    }
+  }
+}
+
+int launch_sat(const float* in, double* out, int n_planes, int H, int W, cudaStream_t stream) {
+  if (n_planes <= 0) return 0;
+  const int grid = (n_planes + kSatWarps - 1) / kSatWarps;
+  const int steps = (W + 127) / 128;
+  if (steps <= 5) sat_kernel<5><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W);
+  else if (steps <= 8) sat_kernel<8><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W);
+  else if (steps <= 16) sat_kernel<16><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W);
+  else return -2;
+  return (int)cudaGetLastError();
+}
+
+__global__ void box_sums_kernel(const double* __restrict__ sat, int planes_per_img, int plane, int H, int W,
+                                const void* __restrict__ boxes, int boxes_f64, const int* __restrict__ counts, int cap,
+                                int n_img, double* __restrict__ sums, double* __restrict__ means) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_img * cap) return;
+  const int img = id / cap, k = id - img * cap;
+  if (counts && k >= counts[img]) return;
+  double x1, y1, x2, y2;
+  load_box<double>(boxes, boxes_f64 != 0, (size_t)id, x1, y1, x2, y2);
+  const Window w = snap_window<double>(x1, y1, x2, y2, W, H);
+  const double* S = sat + ((size_t)img * planes_per_img + plane) * (H + 1) * (W + 1);
+  const int OW = W + 1;
+  double s = 0.0;
+  if (!w.empty())
+    s = S[(size_t)w.y2 * OW + w.x2] - S[(size_t)w.y1 * OW + w.x2] - S[(size_t)w.y2 * OW + w.x1] + S[(size_t)w.y1 * OW + w.x1];
+  sums[id] = s;
+  if (means) means[id] = w.empty() ? 0.0 : s / ((double)w.w() * (double)w.h());
+}
+
+int launch_box_sums(const double* sat, int planes_per_img, int plane, int H, int W, const void* boxes, int boxes_f64,
+                    const int* counts, int cap, int n_img, double* sums, double* means, cudaStream_t stream) {
+  const int total = n_img * cap;
+  if (total <= 0) return 0;
+  box_sums_kernel<<<(total + 255) / 256, 256, 0, stream>>>(sat, planes_per_img, plane, H, W, boxes, boxes_f64, counts, cap,
+                                                            n_img, sums, means);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace unmore

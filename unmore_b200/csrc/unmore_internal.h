@@ -63,6 +63,8 @@ struct CenterParams {
   double filt[25];
 };
 int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream);
+int launch_erode(const unsigned char* in, unsigned char* out, int B, int kernel_size, int num_round, cudaStream_t stream);
+int launch_anti_center(const float* vote, double* out, int B, int H, int W, const double* filt25, cudaStream_t stream);
 
 // ---- lists.cu ------------------------------------------------------------------------
 int launch_prefix_counts(const int* counts, int n_img, int* offsets, cudaStream_t stream);
@@ -101,5 +103,46 @@ struct NmsParams {
   unsigned char* alive_ws;  // [n_img, cap] workspace
 };
 int launch_box_nms(const NmsParams& p, cudaStream_t stream);
+
+// ---- score.cu ------------------------------------------------------------------------
+struct ScoreParams {
+  const float* fields;
+  int n_img, C, H, W, ch_sdf, ch_crow, ch_ccol, ch_exist;
+  const void* boxes;   // [n_img, cap, 4]
+  int boxes_f64;
+  const int* counts;   // nullable
+  int cap;
+  float4* scores;      // [n_img, cap] (existence, center, boundary, 0)
+  float4* tight;       // [n_img, cap] tight box xyxy of the union mask (zeros if empty)
+  int* areas;          // [n_img, cap] set pixels
+  uint32_t* masks;     // nullable [n_img, cap, H, ceil(W/32)] packed union masks
+};
+int launch_score(const ScoreParams& p, cudaStream_t stream);
+
+struct FinalParams {
+  const float4* scores;  // [n_img, cap]
+  const float4* tight;   // [n_img, cap]
+  const int* areas;      // [n_img, cap]
+  const int* keep;       // [n_img, cap] indices kept by NMS, in order
+  const int* keep_counts;
+  int cap, n_img;
+  float existence_thres, center_thres, boundary_thres;  // post_process.py:38-40
+  double* out;           // [n_img, cap, 5] (score, existence, center, boundary, area_score) in keep order
+  float4* bbox_xywh;     // [n_img, cap] COCO-style box in keep order
+  unsigned char* selected;  // nullable [n_img, cap] post_process predicate
+};
+int launch_final_scores(const FinalParams& p, cudaStream_t stream);
+
+// ---- sat.cu --------------------------------------------------------------------------
+int launch_sat(const float* in, double* out, int n_planes, int H, int W, cudaStream_t stream);
+int launch_box_sums(const double* sat, int planes_per_img, int plane, int H, int W, const void* boxes, int boxes_f64,
+                    const int* counts, int cap, int n_img, double* sums, double* means, cudaStream_t stream);
+
+// ---- masks.cu ------------------------------------------------------------------------
+int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, cudaStream_t stream);
+int launch_mask_stats(const uint32_t* masks, int K, int H, int Wp, int* areas, int4* tight, cudaStream_t stream);
+int launch_matrix_nms(const uint32_t* masks, const float4* boxes, int K, int H, int Wp, const float* scores,
+                      const int* areas, const int4* tight, float thr, int* order, unsigned long long* matrix,
+                      int* keep, int* keep_count, cudaStream_t stream);
 
 }  // namespace unmore

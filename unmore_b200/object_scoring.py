@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's ``object_scoring.py`` (class ``Object_Scoring``).
+
+``main_object_scoring`` (object_scoring.py:172-272) scores every discovered box, rasterises
+its union mask on the image canvas, takes the tight box, runs NMS on the tight boxes with
+the boundary score, and emits one annotation per survivor.  Arithmetic runs in
+libunmore_b200.so; masks stay bit-packed on the device ([H, ceil(W/32)] words, LSB = lowest
+x) — the reference's dense [K, H, W] float canvases are never materialised."""
+from __future__ import annotations
+
+import argparse
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+POST_DEFAULTS = dict(existence_score_thres=0.5, center_score_thres=0.8, boundary_score_thres=0.75)  # post_process.py:38-40
+
+
+def unpack_masks(packed: torch.Tensor, width: int) -> np.ndarray:
+    """[K, H, Wp] int32 packed -> uint8 [K, H, W] (host helper for JSON / tests)."""
+    p = packed.cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(p.view(np.uint8), axis=-1, bitorder="little")
+    return bits.reshape(p.shape[0], p.shape[1], -1)[:, :, :width]
+
+
+class Object_Scoring:
+    def __init__(self, args: Optional[argparse.Namespace] = None, device=None, raw_annotations: Optional[dict] = None,
+                 channels: ops.Channels = ops.DEFAULT_CHANNELS):
+        self.args = args if args is not None else argparse.Namespace()
+        for k, v in POST_DEFAULTS.items():
+            if not hasattr(self.args, k):
+                setattr(self.args, k, v)
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise RuntimeError("unmore_b200 has no CPU path; pass a CUDA device")
+        self.channels = channels
+        self.raw_annotations = raw_annotations if raw_annotations is not None else {}
+
+    def _fields(self, image):
+        f = image.to(self.device, torch.float32)
+        return (f.unsqueeze(0) if f.dim() == 3 else f).contiguous()
+
+    def get_prediction_with_proposals(self, image, proposals) -> Dict[str, torch.Tensor]:
+        """object_scoring.py:112-157 (note the (image, proposals) order).  The per-crop maps are
+        never materialised here; the dict carries the three reductions the caller takes of them."""
+        boxes = torch.as_tensor(np.asarray(proposals, dtype=np.float64)).reshape(1, -1, 4).to(self.device)
+        scores, _, _, _ = ops.score_and_rasterise(self._fields(image), boxes, ch=self.channels, want_masks=False)
+        return {"pred_existence_scores": scores[0, :, 0], "max_center_fields_norms": scores[0, :, 1],
+                "max_boundary_distance_values": scores[0, :, 2]}
+
+    def score_batch(self, fields: torch.Tensor, boxes: torch.Tensor, counts: Optional[torch.Tensor] = None,
+                    want_masks: bool = True):
+        """Steps 1-8 of main_object_scoring for a batch: returns a dict of device tensors in NMS keep
+        order: out [B,cap,5] fp64 (score, existence, center, boundary, area_score), bbox [B,cap,4] xywh,
+        selected [B,cap] (post_process predicate), keep [B,cap], keep_counts [B], masks (packed, indexed by
+        the ORIGINAL proposal index: use keep to gather)."""
+        scores, tight, areas, masks = ops.score_and_rasterise(fields, boxes, counts, ch=self.channels, want_masks=want_masks)
+        keep, kc, _ = ops.box_nms(tight, scores[:, :, 2].contiguous(), counts, iou_threshold=0.5, want_boxes=False)
+        out, bbox, sel = ops.final_scores(scores, tight, areas, keep, kc, self.args.existence_score_thres,
+                                          self.args.center_score_thres, self.args.boundary_score_thres)
+        return dict(out=out, bbox=bbox, selected=sel, keep=keep, keep_counts=kc, masks=masks, areas=areas, tight=tight,
+                    scores=scores)
+
+    def score_image(self, image, raw_proposals, image_id=0, with_masks: bool = True) -> List[dict]:
+        """Annotations of one image with the reference's keys (object_scoring.py:257-267);
+        'segmentation' holds {'size': [H, W], 'mask': uint8 [H, W]} instead of a pycocotools RLE string."""
+        fields = self._fields(image)
+        H, W = fields.shape[-2], fields.shape[-1]
+        if len(raw_proposals) == 0:
+            return []
+        boxes = torch.as_tensor(np.asarray(raw_proposals, dtype=np.float64)).reshape(1, -1, 4).to(self.device)
+        r = self.score_batch(fields, boxes, None, want_masks=with_masks)
+        n = int(r["keep_counts"][0])
+        keep = r["keep"][0, :n].long()
+        out = r["out"][0, :n].cpu().numpy()
+        bbox = r["bbox"][0, :n].cpu().numpy()
+        dense = unpack_masks(r["masks"][0][keep], W) if with_masks else None
+        anns = []
+        for i in range(n):
+            ann = {"image_id": image_id, "category_id": 1, "score": out[i, 0], "bbox": [v for v in bbox[i]],
+                   "existence_score": np.float32(out[i, 1]), "center_score": np.float32(out[i, 2]),
+                   "boundary_score": np.float32(out[i, 3]), "area_score": out[i, 4]}
+            if with_masks:
+                ann["segmentation"] = {"size": [H, W], "mask": dense[i]}
+            anns.append(ann)
+        return anns
+
+    def main_object_scoring(self, images, image_ids) -> List[dict]:
+        """object_scoring.py:172-272 over in-memory field stacks; returns ``out_annotations``."""
+        out = []
+        for img, iid in zip(images, image_ids):
+            raw = self.raw_annotations.get(str(int(iid)))
+            if raw is None:
+                continue
+            out.extend(self.score_image(img, raw, image_id=int(iid)))
+        return out

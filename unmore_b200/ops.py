@@ -30,6 +30,60 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class StageTimer:
+    """CUDA-event timing of every C-ABI call, on the stream the kernels are launched on.
+    bench.py installs one (``ops.set_timer``) for the timed region; ``summary()`` synchronises."""
+
+    def __init__(self):
+        self.events = []   # (name, start, end, kernels)
+        self.launches = 0
+
+    def record(self, name, kernels, fn, *args):
+        st = torch.cuda.current_stream()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn(name, *args)
+        b.record(st)
+        self.events.append((name, a, b))
+        self.launches += kernels
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0})
+            d["ms"] += a.elapsed_time(b)
+            d["calls"] += 1
+        return out
+
+
+_timer: Optional[StageTimer] = None
+LAUNCHES = 0  # kernels launched through the C ABI since import (gpu_launches in bench.py)
+
+# kernels per C-ABI call (memsets not counted); +1 when a counts prefix is built
+_KERNELS = {"unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
+            "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
+            "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_box_nms_matrix": 3,
+            "unmore_score_and_rasterise": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_box_sums": 1,
+            "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3}
+
+
+def set_timer(t: Optional[StageTimer]):
+    global _timer
+    _timer = t
+
+
+def _call(name, *args, counts=None):
+    global LAUNCHES
+    k = _KERNELS[name] + (1 if counts is not None else 0)
+    LAUNCHES += k
+    if _timer is not None:
+        _timer.record(name, k, _lib.call, *args)
+    else:
+        _lib.call(name, *args)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -66,8 +120,8 @@ def existence_scores(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANNELS
     _check_counts(counts, n_img)
     ws = workspace(n_img, fields.device) if ws is None else ws
     out = torch.zeros((n_img, cap), dtype=torch.float32, device=fields.device) if out is None else out
-    _lib.call("unmore_existence_scores", fields.data_ptr(), n_img, C, H, W, ch.exist, boxes.data_ptr(), f64,
-              _ptr(counts), cap, out.data_ptr(), ws.data_ptr(), _stream())
+    _call("unmore_existence_scores", fields.data_ptr(), n_img, C, H, W, ch.exist, boxes.data_ptr(), f64,
+              _ptr(counts), cap, out.data_ptr(), ws.data_ptr(), _stream(), counts=counts)
     return out
 
 
@@ -81,9 +135,9 @@ def center_reasoning(fields, boxes, counts=None, thr: float = 0.009, ch: Channel
     maxv = torch.zeros((n_img, cap), dtype=torch.float64, device=dev)
     argmax = torch.full((n_img, cap), -1, dtype=torch.int32, device=dev)
     splits = torch.zeros((n_img, cap, 4, 4), dtype=torch.float64, device=dev) if want_splits else None
-    _lib.call("unmore_center_reasoning", fields.data_ptr(), n_img, C, H, W, ch.sdf, ch.center_row, ch.center_col,
+    _call("unmore_center_reasoning", fields.data_ptr(), n_img, C, H, W, ch.sdf, ch.center_row, ch.center_col,
               boxes.data_ptr(), f64, _ptr(counts), cap, float(thr), maxv.data_ptr(), argmax.data_ptr(),
-              _ptr(splits), ws.data_ptr(), _stream())
+              _ptr(splits), ws.data_ptr(), _stream(), counts=counts)
     return maxv, argmax, splits
 
 
@@ -99,10 +153,10 @@ def boundary_refine(fields, boxes, counts=None, n_round: int = 50, apply_small_f
     out = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
     labels = torch.full((n_img, cap), -2.0, dtype=torch.float32, device=dev)
     rounds = torch.zeros((n_img, cap), dtype=torch.int32, device=dev) if want_rounds else None
-    _lib.call("unmore_boundary_refine", fields.data_ptr(), n_img, C, H, W, ch.sdf, boxes.data_ptr(), f64,
+    _call("unmore_boundary_refine", fields.data_ptr(), n_img, C, H, W, ch.sdf, boxes.data_ptr(), f64,
               _ptr(counts), cap, int(n_round), int(apply_small_filter), int(early_exit), float(proposal_area_thres),
               float(max_sdf_thres), float(max_shrink_threshold), float(delta_ratio), out.data_ptr(),
-              labels.data_ptr(), _ptr(rounds), ws.data_ptr(), _stream())
+              labels.data_ptr(), _ptr(rounds), ws.data_ptr(), _stream(), counts=counts)
     return out, labels, rounds
 
 
@@ -113,7 +167,7 @@ def update_bbox_from_tiles(tiles: torch.Tensor):
     m = tiles.shape[0]
     deltas = torch.zeros((m, 4), dtype=torch.float32, device=tiles.device)
     mx = torch.zeros((m,), dtype=torch.float32, device=tiles.device)
-    _lib.call("unmore_update_bbox_from_tiles", tiles.data_ptr(), m, deltas.data_ptr(), mx.data_ptr(), _stream())
+    _call("unmore_update_bbox_from_tiles", tiles.data_ptr(), m, deltas.data_ptr(), mx.data_ptr(), _stream())
     return deltas, mx
 
 
@@ -137,7 +191,7 @@ def compact_boxes(inp, counts_in, mode, pred, thr=0.0, group=1, out=None, counts
     if counts_out is None:
         counts_out = torch.zeros((n_img,), dtype=torch.int32, device=dev)
     index = torch.full((n_img, cap_out), -1, dtype=torch.int32, device=dev) if want_index else None
-    _lib.call("unmore_compact_boxes", inp.data_ptr(), int(inp.dtype == torch.float64), _ptr(counts_in), cap_in,
+    _call("unmore_compact_boxes", inp.data_ptr(), int(inp.dtype == torch.float64), _ptr(counts_in), cap_in,
               group, mode, pred.data_ptr(), float(thr), out.data_ptr(), int(out.dtype == torch.float64), cap_out,
               counts_out.data_ptr(), int(append), _ptr(index), n_img, _stream())
     return out, counts_out, index
@@ -155,6 +209,136 @@ def box_nms(boxes, scores=None, counts=None, iou_threshold: float = 0.5, want_bo
     kb = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev) if want_boxes else None
     if scores is not None:
         scores = scores.contiguous().to(torch.float32)
-    _lib.call("unmore_box_nms", boxes.data_ptr(), _ptr(scores), _ptr(counts), cap, n_img, float(iou_threshold),
+    _call("unmore_box_nms", boxes.data_ptr(), _ptr(scores), _ptr(counts), cap, n_img, float(iou_threshold),
               keep.data_ptr(), kc.data_ptr(), _ptr(kb), order.data_ptr(), _stream())
     return keep, kc, kb
+
+
+def box_nms_matrix(boxes, scores=None, iou_threshold: float = 0.5):
+    """One list of K boxes [K,4] fp32 -> kept indices (int64, descending-score order)."""
+    boxes = boxes.contiguous().to(torch.float32)
+    K = boxes.shape[0]
+    dev = boxes.device
+    nblk = (K + 63) // 64
+    order = torch.empty((max(K, 1),), dtype=torch.int32, device=dev)
+    matrix = torch.empty((max(K * nblk, 1),), dtype=torch.int64, device=dev)
+    keep = torch.full((max(K, 1),), -1, dtype=torch.int32, device=dev)
+    kc = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if scores is not None:
+        scores = scores.contiguous().to(torch.float32)
+    _call("unmore_box_nms_matrix", boxes.data_ptr(), _ptr(scores), K, float(iou_threshold), order.data_ptr(),
+              matrix.data_ptr(), keep.data_ptr(), kc.data_ptr(), _stream())
+    return keep[: int(kc.item())].to(torch.int64)
+
+
+def batch_erode(masks_u8: torch.Tensor, kernel_size: int = 9, num_round: int = 3) -> torch.Tensor:
+    m = masks_u8.contiguous()
+    B, H, W = m.shape
+    out = torch.empty_like(m)
+    _call("unmore_batch_erode", m.data_ptr(), B, H, W, int(kernel_size), int(num_round), out.data_ptr(), _stream())
+    return out
+
+
+def anti_center_map(vote_maps: torch.Tensor, kernel_size: int = 5) -> torch.Tensor:
+    v = vote_maps.contiguous().to(torch.float32)
+    B, _, H, W = v.shape
+    out = torch.empty((B, H, W), dtype=torch.float64, device=v.device)
+    _call("unmore_anti_center_map", v.data_ptr(), B, H, W, int(kernel_size), out.data_ptr(), _stream())
+    return out
+
+
+def score_and_rasterise(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANNELS, want_masks: bool = True):
+    """-> scores [n_img,cap,4] (existence, center, boundary, 0), tight xyxy [n_img,cap,4], areas [n_img,cap],
+    packed masks [n_img,cap,H,ceil(W/32)] int32 (or None)."""
+    n_img, C, H, W = _check_fields(fields)
+    cap, f64 = _check_boxes(boxes, n_img)
+    _check_counts(counts, n_img)
+    dev = fields.device
+    scores = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
+    tight = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
+    areas = torch.zeros((n_img, cap), dtype=torch.int32, device=dev)
+    masks = torch.zeros((n_img, cap, H, (W + 31) // 32), dtype=torch.int32, device=dev) if want_masks else None
+    if cap > 0:
+        _call("unmore_score_and_rasterise", fields.data_ptr(), n_img, C, H, W, ch.sdf, ch.center_row, ch.center_col,
+                  ch.exist, boxes.data_ptr(), f64, _ptr(counts), cap, scores.data_ptr(), tight.data_ptr(),
+                  areas.data_ptr(), _ptr(masks), _stream())
+    return scores, tight, areas, masks
+
+
+def final_scores(scores, tight, areas, keep, keep_counts, existence_score_thres=0.5, center_score_thres=0.8,
+                 boundary_score_thres=0.75):
+    """-> out [n_img,cap,5] fp64 (score, existence, center, boundary, area_score), bbox xywh [n_img,cap,4],
+    selected [n_img,cap] uint8 — all in NMS keep order."""
+    n_img, cap = areas.shape
+    dev = areas.device
+    out = torch.zeros((n_img, cap, 5), dtype=torch.float64, device=dev)
+    bbox = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
+    sel = torch.zeros((n_img, cap), dtype=torch.uint8, device=dev)
+    if cap > 0:
+        _call("unmore_final_scores", scores.data_ptr(), tight.data_ptr(), areas.data_ptr(), keep.data_ptr(),
+                  keep_counts.data_ptr(), cap, n_img, float(existence_score_thres), float(center_score_thres),
+                  float(boundary_score_thres), out.data_ptr(), bbox.data_ptr(), sel.data_ptr(), _stream())
+    return out, bbox, sel
+
+
+def sat_build(planes: torch.Tensor) -> torch.Tensor:
+    """[..., H, W] fp32 CUDA -> [..., H+1, W+1] fp64 exclusive 2-D prefix sums."""
+    if not planes.is_cuda or planes.dtype != torch.float32:
+        raise _lib.UnmoreError("sat_build needs a CUDA fp32 tensor")
+    p = planes.contiguous()
+    H, W = p.shape[-2], p.shape[-1]
+    n = p.numel() // (H * W) if H * W else 0
+    out = torch.empty(p.shape[:-2] + (H + 1, W + 1), dtype=torch.float64, device=p.device)
+    _call("unmore_sat_build", p.data_ptr(), n, H, W, out.data_ptr(), _stream())
+    return out
+
+
+def box_sums(sat: torch.Tensor, plane: int, boxes: torch.Tensor, counts=None):
+    """sat [n_img, P, H+1, W+1] fp64, boxes [n_img, cap, 4] -> (sums, means) [n_img, cap] fp64."""
+    n_img, P, H1, W1 = sat.shape
+    cap, f64 = _check_boxes(boxes, n_img)
+    sums = torch.zeros((n_img, cap), dtype=torch.float64, device=sat.device)
+    means = torch.zeros((n_img, cap), dtype=torch.float64, device=sat.device)
+    if cap > 0:
+        _call("unmore_box_sums", sat.data_ptr(), n_img, P, int(plane), H1 - 1, W1 - 1, boxes.data_ptr(), f64,
+                  _ptr(counts), cap, sums.data_ptr(), means.data_ptr(), _stream())
+    return sums, means
+
+
+def mask_pack(dense_u8: torch.Tensor) -> torch.Tensor:
+    """[K, H, W] uint8/bool CUDA -> [K, H, ceil(W/32)] int32 bit-packed (LSB = lowest x)."""
+    d = dense_u8
+    if d.dtype == torch.bool:
+        d = d.view(torch.uint8)
+    if not d.is_cuda or d.dtype != torch.uint8:
+        raise _lib.UnmoreError("mask_pack needs a CUDA uint8/bool tensor")
+    d = d.contiguous()
+    K, H, W = d.shape
+    out = torch.empty((K, H, (W + 31) // 32), dtype=torch.int32, device=d.device)
+    _call("unmore_mask_pack", d.data_ptr(), K, H, W, out.data_ptr(), _stream())
+    return out
+
+
+def mask_stats(packed: torch.Tensor, W: int):
+    K, H, _ = packed.shape
+    areas = torch.zeros((K,), dtype=torch.int32, device=packed.device)
+    tight = torch.zeros((K, 4), dtype=torch.int32, device=packed.device)
+    _call("unmore_mask_stats", packed.data_ptr(), K, H, W, areas.data_ptr(), tight.data_ptr(), _stream())
+    return areas, tight
+
+
+def mask_nms(packed: torch.Tensor, W: int, scores: torch.Tensor, iou_threshold: float = 0.5, stats=None):
+    """Mask-IoU NMS on packed masks [K, H, ceil(W/32)]: kept indices, descending-score order (int64)."""
+    packed = packed.contiguous()
+    K, H, _ = packed.shape
+    dev = packed.device
+    areas, tight = stats if stats is not None else mask_stats(packed, W)
+    nblk = (K + 63) // 64
+    order = torch.empty((max(K, 1),), dtype=torch.int32, device=dev)
+    matrix = torch.empty((max(K * nblk, 1),), dtype=torch.int64, device=dev)
+    keep = torch.full((max(K, 1),), -1, dtype=torch.int32, device=dev)
+    kc = torch.zeros((1,), dtype=torch.int32, device=dev)
+    scores = scores.contiguous().to(torch.float32)
+    _call("unmore_mask_nms", packed.data_ptr(), K, H, W, scores.data_ptr(), areas.data_ptr(), tight.data_ptr(),
+              float(iou_threshold), order.data_ptr(), matrix.data_ptr(), keep.data_ptr(), kc.data_ptr(), _stream())
+    return keep[: int(kc.item())].to(torch.int64)
