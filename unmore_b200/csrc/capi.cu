@@ -115,6 +115,7 @@ int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W,
   p.boxes = boxes; p.boxes_f64 = boxes_f64; p.thr = center_score_max_thres;
   p.max_values = max_values_out; p.argmax = argmax_out; p.splits = splits_out;
   anti_center_filter(p.filt);
+  for (int i = 0; i < 25; ++i) p.filt32[i] = (float)p.filt[i];  // exact: the table is fp32-valued
   if (int e = make_worklist(p.work, counts, n_img, cap, ws, s)) return e;
   return cuda_fail(launch_center(p, num_sms(), s), "center_kernel");
 }
@@ -161,8 +162,10 @@ int unmore_compact_boxes(const void* in, int in_f64, const int* counts_in, int c
 
 int unmore_box_nms(const float* boxes, const float* scores, const int* counts, int cap, int n_img, float iou_threshold,
                    int* keep_out, int* keep_counts_out, float* boxes_out, int* order_ws, unmore_stream_t stream) {
-  if (!boxes || !keep_out || !keep_counts_out || !order_ws || cap < 0 || n_img < 0)
-    return fail(UNMORE_E_INVALID, "unmore_box_nms: bad argument");
+  if (cap < 0 || n_img < 0 || (n_img > 0 && !keep_counts_out)) return fail(UNMORE_E_INVALID, "unmore_box_nms: bad argument");
+  if (n_img == 0) return 0;
+  if (cap == 0) return cuda_fail((int)cudaMemsetAsync(keep_counts_out, 0, sizeof(int) * n_img, (cudaStream_t)stream), "memset");
+  if (!boxes || !keep_out || !order_ws) return fail(UNMORE_E_INVALID, "unmore_box_nms: bad argument");
   if (cap > 32768) return fail(UNMORE_E_CAPACITY, "unmore_box_nms: cap %d > 32768", cap);
   NmsParams p{};
   p.boxes = reinterpret_cast<const float4*>(boxes); p.scores = scores; p.counts = counts; p.cap = cap; p.n_img = n_img;

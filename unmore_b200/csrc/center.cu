@@ -28,6 +28,8 @@ struct CenterSmem {
   uint32_t ero[kCrop][4];    // fully eroded mask
   double red_val[kCenterWarps];
   int red_idx[kCenterWarps];
+  float red_f[kCenterWarps];
+  float bcast_f[2];
 };
 
 typedef unsigned __int128 u128;
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       p1.init(base + p.ch_ccol * plane_sz, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
+      float cabs = 0.f;  // max |center field| over the staged window: scales the fp32 screening margin
       for (int ii = 0; ii < kCrop / kCenterWarps; ++ii) {
         const int i = warp * (kCrop / kCenterWarps) + ii;
         const AxisTap v = axis_tap(scale_y, i, in_h);
@@ -81,13 +84,15 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int j = 4 * lane + c;
-          // ||c|| > 0.5 exactly as torch.norm: round(a*a) + round(b*b), IEEE sqrt
-          const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c])));
-          const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (nrm > 0.5f);
+          // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
+          // equivalent threshold on the squared norm
+          const float sq = __fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c]));
+          const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
           nib |= (on ? 1u : 0u) << c;
           if (i >= kWinLo && i < kWinHi && j >= kWinLo && j < kWinHi) {
             sm.c0[(i - kWinLo) * kWin + (j - kWinLo)] = a[c];
             sm.c1[(i - kWinLo) * kWin + (j - kWinLo)] = b[c];
+            cabs = fmaxf(cabs, fmaxf(fabsf(a[c]), fabsf(b[c])));
           }
         }
         // gather 8 lanes' nibbles into one 32-bit word (lanes 0, 8, 16, 24 end up holding words 0..3)
@@ -97,6 +102,8 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         w |= __shfl_down_sync(kFullMask, w, 4) << 16;
         if ((lane & 7) == 0) sm.mask[i][lane >> 3] = w;
       }
+      cabs = warp_max(cabs);
+      if (lane == 0) sm.red_f[warp] = cabs;
       __syncthreads();
       // ---- 2. erosion: 25-runs along rows, then AND of 25 rows
       if (tid < kCrop) {
@@ -116,26 +123,107 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         store_row(sm.ero[tid], e);
       }
       __syncthreads();
-      // ---- 3. anti-center map on surviving pixels, fp64, then masked max / first arg-max
-      constexpr int kInner = kCrop - 2 * kErode;  // 104: only rows/cols 12..115 can survive
-      double tbest = 0.0;
-      int tidx = -1;
-      for (int q = tid; q < kInner * kInner; q += kCenterThreads) {
-        const int r = kErode + q / kInner, c = kErode + q % kInner;
-        if (!((sm.ero[r][c >> 5] >> (c & 31)) & 1u)) continue;
-        double acc = 0.0;
+      // ---- 3. anti-center map on surviving pixels, then masked max / first arg-max.
+      // The map is needed in fp64 only where it can decide the result (the maximum).  So: (a) an
+      // fp32 register-tiled 5x5x2 correlation over 1x8 pixel strips that contain surviving pixels
+      // gives a screening maximum M32; (b) every surviving pixel whose fp32 value is within a
+      // rigorous rounding margin of M32 is re-evaluated exactly as the reference does (fp64
+      // products of the fp32-normalised filter, / 24) and competes for (max, first index).
+      constexpr int kInner = kCrop - 2 * kErode;   // 104: only rows/cols 12..115 can survive
+      constexpr int kStrips = kInner / 8;          // 13 strips of 8 columns per row
+      constexpr int kMaxOwn = (kInner * kStrips + kCenterThreads - 1) / kCenterThreads;  // 3
+      float own_max[kMaxOwn];
+      auto strip_bits = [&](int r, int k) -> uint32_t {
+        const int c = kErode + 8 * k;              // first column of the strip
+        const uint32_t lo = sm.ero[r][c >> 5], hi = sm.ero[r][min((c >> 5) + 1, 3)];
+        return (__funnelshift_r(lo, hi, c & 31)) & 0xffu;
+      };
+      auto strip_scores = [&](int r, int k, float acc[8]) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) acc[x] = 0.f;
+        const int c = kErode + 8 * k;
 #pragma unroll
         for (int di = 0; di < 5; ++di) {
+          const int o = (r + di - 2 - kWinLo) * kWin + (c - 2 - kWinLo);  // multiple of 4 floats
+          float v0[12], v1[12];
+#pragma unroll
+          for (int q4 = 0; q4 < 3; ++q4) {
+            const float4 t0 = *reinterpret_cast<const float4*>(&sm.c0[o + 4 * q4]);
+            const float4 t1 = *reinterpret_cast<const float4*>(&sm.c1[o + 4 * q4]);
+            v0[4 * q4] = t0.x; v0[4 * q4 + 1] = t0.y; v0[4 * q4 + 2] = t0.z; v0[4 * q4 + 3] = t0.w;
+            v1[4 * q4] = t1.x; v1[4 * q4 + 1] = t1.y; v1[4 * q4 + 2] = t1.z; v1[4 * q4 + 3] = t1.w;
+          }
 #pragma unroll
           for (int dj = 0; dj < 5; ++dj) {
             if (di == 2 && dj == 2) continue;
-            const int o = (r + di - 2 - kWinLo) * kWin + (c + dj - 2 - kWinLo);
-            acc = fma(p.filt[di * 5 + dj], (double)sm.c0[o], acc);   // f[0][i][j] = (2-i)/n
-            acc = fma(p.filt[dj * 5 + di], (double)sm.c1[o], acc);   // f[1][i][j] = (2-j)/n
+            const float f0 = p.filt32[di * 5 + dj], f1 = p.filt32[dj * 5 + di];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) acc[x] = fmaf(f0, v0[x + dj], fmaf(f1, v1[x + dj], acc[x]));
           }
         }
-        acc = __ddiv_rn(acc, 24.0);
-        if (tidx < 0 || acc > tbest) { tbest = acc; tidx = r * kCrop + c; }  // q ascending == flat index ascending
+      };
+      float m32 = -INFINITY;
+#pragma unroll
+      for (int m = 0; m < kMaxOwn; ++m) {
+        own_max[m] = -INFINITY;
+        const int q = tid + m * kCenterThreads;
+        if (q < kInner * kStrips) {
+          const int r = kErode + q / kStrips, k = q % kStrips;
+          const uint32_t bits = strip_bits(r, k);
+          if (bits) {
+            float acc[8];
+            strip_scores(r, k, acc);
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              if ((bits >> x) & 1u) own_max[m] = fmaxf(own_max[m], acc[x]);
+            m32 = fmaxf(m32, own_max[m]);
+          }
+        }
+      }
+      m32 = warp_max(m32);
+      float cmax = 0.f;
+      if (lane == 0) sm.red_val[warp] = (double)m32;
+      __syncthreads();
+      if (tid == 0) {
+        float mm = -INFINITY, cm = 0.f;
+        for (int w = 0; w < kCenterWarps; ++w) { mm = fmaxf(mm, (float)sm.red_val[w]); cm = fmaxf(cm, sm.red_f[w]); }
+        sm.bcast_f[0] = mm; sm.bcast_f[1] = cm;
+      }
+      __syncthreads();
+      m32 = sm.bcast_f[0];
+      cmax = sm.bcast_f[1];
+      // |fp32 sum - exact sum| <= 48 ops * 2^-24 * sum|f||c| <= 48 * 2^-24 * 31 * cmax (before the / 24);
+      // a tie of the true maximum can sit at most twice that below M32.  Padded x4.
+      const float margin = 8.0f * 48.0f * 5.9604645e-08f * 31.0f * cmax;
+      double tbest = 0.0;
+      int tidx = -1;
+#pragma unroll
+      for (int m = 0; m < kMaxOwn; ++m) {
+        if (!(own_max[m] >= m32 - margin) || m32 == -INFINITY) continue;
+        const int q = tid + m * kCenterThreads;
+        const int r = kErode + q / kStrips, k = q % kStrips;
+        const uint32_t bits = strip_bits(r, k);
+        float acc[8];
+        strip_scores(r, k, acc);
+#pragma unroll 1
+        for (int x = 0; x < 8; ++x) {
+          if (!((bits >> x) & 1u) || !(acc[x] >= m32 - margin)) continue;
+          const int c = kErode + 8 * k + x;
+          double e = 0.0;
+#pragma unroll
+          for (int di = 0; di < 5; ++di) {
+#pragma unroll
+            for (int dj = 0; dj < 5; ++dj) {
+              if (di == 2 && dj == 2) continue;
+              const int o = (r + di - 2 - kWinLo) * kWin + (c + dj - 2 - kWinLo);
+              e = fma(p.filt[di * 5 + dj], (double)sm.c0[o], e);   // f[0][i][j] = (2-i)/n
+              e = fma(p.filt[dj * 5 + di], (double)sm.c1[o], e);   // f[1][i][j] = (2-j)/n
+            }
+          }
+          e = __ddiv_rn(e, 24.0);
+          const int flat = r * kCrop + c;
+          if (tidx < 0 || e > tbest || (e == tbest && flat < tidx)) { tbest = e; tidx = flat; }
+        }
       }
       // block arg-max, ties -> smallest flat index (torch.argmax returns the first maximum)
 #pragma unroll
@@ -144,6 +232,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const int oi = __shfl_xor_sync(kFullMask, tidx, o);
         if (oi >= 0 && (tidx < 0 || ov > tbest || (ov == tbest && oi < tidx))) { tbest = ov; tidx = oi; }
       }
+      __syncthreads();  // red_val is reused
       if (lane == 0) { sm.red_val[warp] = tbest; sm.red_idx[warp] = tidx; }
       __syncthreads();
       if (tid == 0) {

@@ -24,6 +24,10 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // sigmoid(x) > 0.5 on the reference's CPU path  <=>  x > 1.5 * 2^-24 (0x33c00000); pinned in
 // tests/test_oracle_golden.py::test_sigmoid_threshold_constant
 #define UNMORE_SIGMOID_HALF_THRESHOLD 8.94069671630859375e-08f
+// ||c|| > 0.5 with ||c|| = sqrt_rn(s), s = round(a*a) + round(b*b)  <=>  s > 0.25 * (1 + 2^-23)
+// (0x3e800001): the first float whose correctly rounded square root exceeds 0.5 is 0x3e800002.
+// Lets the mask kernels skip the IEEE square root; pinned in tests/test_oracle_golden.py.
+#define UNMORE_NORM_HALF_SQ_THRESHOLD 0.2500000298023223876953125f
 
 struct AxisTap {
   int i0, i1;

@@ -65,17 +65,15 @@ struct Deltas {
 // a10 on one proposal.  `src.row(lane, i, out)` yields S[i][4*lane .. 4*lane+3].
 template <class RowSrc>
 __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, int lane) {
-  float cur[4], nxt[4], top[4], bot[4];
-  src.row(lane, 0, cur);
+  float ra[4], rb[4], top[4], bot[4];
+  src.row(lane, 0, ra);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) top[c] = cur[c];
-  float mx = fmaxf(fmaxf(cur[0], cur[1]), fmaxf(cur[2], cur[3]));
+  for (int c = 0; c < 4; ++c) top[c] = bot[c] = ra[c];
+  float mx = fmaxf(fmaxf(ra[0], ra[1]), fmaxf(ra[2], ra[3]));
   double dA = 0.0, dAg = 0.0, dB = 0.0, dBg = 0.0;
   float fA = 0.f, fAg = 0.f, fB = 0.f, fBg = 0.f;
-  // fp32 partial sums are flushed into fp64 every 8 rows (32 px per lane): keeps the
-  // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
-  for (int i = 0; i < kCrop - 1; ++i) {
-    src.row(lane, i + 1, nxt);
+  // One output row of the 127x127 region: cur = S[i][.], nxt = S[i+1][.].
+  auto process = [&](const float (&cur)[4], const float (&nxt)[4], int i) {
     const float right = __shfl_down_sync(kFullMask, cur[0], 1);
     if (lane == 0) cols.left[i] = cur[0];
     if (lane == 31) cols.right[i] = cur[2];
@@ -84,12 +82,10 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
       const float s = cur[c];
       const float dxv = (c < 3 ? cur[c + 1] : right) - s;
       const float dyv = nxt[c] - s;
-      // ||grad|| as torch.norm computes it: round(dy*dy) + round(dx*dx), then sqrt
-      const float g = sqrt_approx(__fadd_rn(__fmul_rn(dyv, dyv), __fmul_rn(dxv, dxv)));
+      const float g = sqrt_approx(fmaf(dyv, dyv, dxv * dxv));  // ||grad||; only feeds the averaged sums
       const float a = soft_fg(s);
       const float b = 1.f - a;
-      const bool valid = (c < 3) || (lane < 31);  // column 127 is outside the 127x127 region
-      if (valid) {
+      if ((c < 3) || (lane < 31)) {  // column 127 is outside the 127x127 region
         fA += a;
         fAg = fmaf(a, g, fAg);
         fB += b;
@@ -97,17 +93,27 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
       }
       mx = fmaxf(mx, nxt[c]);
     }
-    if ((i & 7) == 7 || i == kCrop - 2) {
-      dA += (double)fA; dAg += (double)fAg; dB += (double)fB; dBg += (double)fBg;
-      fA = fAg = fB = fBg = 0.f;
-    }
-    if (i == kCrop - 2) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) bot[c] = cur[c];  // row 126
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) cur[c] = nxt[c];
+  };
+  // fp32 partial sums are flushed into fp64 every 8 rows (32 px per lane): keeps the
+  // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
+  auto flush = [&]() {
+    dA += (double)fA; dAg += (double)fAg; dB += (double)fB; dBg += (double)fBg;
+    fA = fAg = fB = fBg = 0.f;
+  };
+  // rows ping-pong between ra / rb so no register copies are needed
+  for (int i = 0; i < kCrop - 2; i += 2) {
+    src.row(lane, i + 1, rb);
+    process(ra, rb, i);
+    src.row(lane, i + 2, ra);
+    process(rb, ra, i + 1);
+    if ((i & 7) == 6) flush();
   }
+  // i = 126: ra holds row 126
+#pragma unroll
+  for (int c = 0; c < 4; ++c) bot[c] = ra[c];
+  src.row(lane, kCrop - 1, rb);
+  process(ra, rb, kCrop - 2);
+  flush();
   Deltas d;
   d.max_sdf = warp_max(mx);
   const float sumA = (float)warp_sum(dA);
@@ -206,7 +212,7 @@ __device__ __forceinline__ int one_round(const RefineParams& p, const float* pla
 
 constexpr int kRefineWarps = 8;
 
-__global__ void __launch_bounds__(kRefineWarps * 32) refine_kernel(const RefineParams p) {
+__global__ void __launch_bounds__(kRefineWarps * 32, 3) refine_kernel(const RefineParams p) {
   __shared__ BorderCols cols_all[kRefineWarps];
   const int lane = threadIdx.x & 31;
   BorderCols& cols = cols_all[threadIdx.x >> 5];
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) tiles_kernel(const TilePara
 }
 
 int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream) {
-  const int ctas = num_sms * 4;  // 32 warps/SM resident; warps pull proposals dynamically
+  const int ctas = num_sms * 3;  // 24 warps/SM resident (<= 85 registers); warps pull proposals dynamically
   refine_kernel<<<ctas, kRefineWarps * 32, 0, stream>>>(p);
   return (int)cudaGetLastError();
 }

@@ -12,14 +12,15 @@ namespace unmore {
 
 // Column taps of this lane for the current window (shared by all channels).
 struct ColTaps {
-  int x0[4], x1[4];
+  int x0[4];
+  bool two[4];  // second tap is x0+1 (false only on the clamped right edge, where it repeats x0)
   float w0[4], w1[4];
   __device__ __forceinline__ void init(int lane, int in_w) {
     const float scale = __fdiv_rn((float)in_w, (float)kCrop);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       AxisTap t = axis_tap(scale, 4 * lane + c, in_w);
-      x0[c] = t.i0; x1[c] = t.i1; w0[c] = t.l0; w1[c] = t.l1;
+      x0[c] = t.i0; two[c] = t.i1 != t.i0; w0[c] = t.l0; w1[c] = t.l1;
     }
   }
 };
@@ -37,9 +38,17 @@ struct PlaneRows {
     cy0 = cy1 = -1;
   }
   __device__ __forceinline__ void hrow(const ColTaps& t, int y, float out[4]) const {
-    const float* p = origin + (size_t)y * stride;
+    // 32-bit element offsets from the window origin: one IADD + one IMAD.WIDE per column, the
+    // second tap rides on the same address (+4 bytes, predicated off on the clamped edge)
+    const int ro = y * stride;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = lerp_h(__ldg(p + t.x0[c]), __ldg(p + t.x1[c]), t.w0[c], t.w1[c]);
+    for (int c = 0; c < 4; ++c) {
+      const float* q = origin + (ro + t.x0[c]);
+      const float v0 = __ldg(q);
+      float v1 = v0;
+      if (t.two[c]) v1 = __ldg(q + 1);
+      out[c] = lerp_h(v0, v1, t.w0[c], t.w1[c]);
+    }
   }
   // S[i][4l..4l+3] for the output row whose vertical tap is `v`
   __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[4]) {

@@ -61,6 +61,7 @@ struct CenterParams {
   // F.normalize(filter, dim=1) in fp32, then .double() (object_reasoning.py:372-373):
   // filt[i*5+j] = (2-i)/sqrt((2-i)^2+(2-j)^2); channel 1 uses the transposed entry
   double filt[25];
+  float filt32[25];    // the same values before the cast to double (fp32 screening pass)
 };
 int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream);
 int launch_erode(const unsigned char* in, unsigned char* out, int B, int kernel_size, int num_round, cudaStream_t stream);
