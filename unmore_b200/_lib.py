@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunmore_b200.so")
+LIB_PATH = os.environ.get("UNMORE_B200_LIB", os.path.join(_HERE, "libunmore_b200.so"))  # override: A/B builds
 
 _p = C.c_void_p
 _i = C.c_int

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
     if (!win.empty()) {
       // ---- 1. resample 3 channels; warp w owns output rows 8w .. 8w+7
       ColTaps taps;
-      taps.init(lane, win.w());
+      taps.init<kStrided>(lane, win.w());
       const size_t plane_sz = (size_t)p.H * p.W;
       const float* base = p.fields + (size_t)img * p.C * plane_sz;
       PlaneRows ps, p0, p1;
@@ -80,27 +80,21 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         ps.row(taps, v, s);
         p0.row(taps, v, a);
         p1.row(taps, v, b);
-        uint32_t nib = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int j = 4 * lane + c;
+          const int j = lane + 32 * c;
           // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
           // equivalent threshold on the squared norm
           const float sq = __fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c]));
           const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
-          nib |= (on ? 1u : 0u) << c;
+          const uint32_t word = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
+          if (lane == 0) sm.mask[i][c] = word;
           if (i >= kWinLo && i < kWinHi && j >= kWinLo && j < kWinHi) {
             sm.c0[(i - kWinLo) * kWin + (j - kWinLo)] = a[c];
             sm.c1[(i - kWinLo) * kWin + (j - kWinLo)] = b[c];
             cabs = fmaxf(cabs, fmaxf(fabsf(a[c]), fabsf(b[c])));
           }
         }
-        // gather 8 lanes' nibbles into one 32-bit word (lanes 0, 8, 16, 24 end up holding words 0..3)
-        uint32_t w = nib;
-        w |= __shfl_down_sync(kFullMask, w, 1) << 4;
-        w |= __shfl_down_sync(kFullMask, w, 2) << 8;
-        w |= __shfl_down_sync(kFullMask, w, 4) << 16;
-        if ((lane & 7) == 0) sm.mask[i][lane >> 3] = w;
       }
       cabs = warp_max(cabs);
       if (lane == 0) sm.red_f[warp] = cabs;

@@ -46,8 +46,24 @@ struct CropRows {  // crop window of the boundary-distance channel, resampled on
   PlaneRows plane;
   float scale_y;
   int in_h;
+  int pf_off;   // this lane's 128-byte line of a source row (element offset), or -1
+  __device__ __forceinline__ void init_prefetch(int lane, int in_w) {
+    pf_off = (32 * lane < in_w + 32) ? 32 * lane : -1;
+  }
   __device__ __forceinline__ void row(int /*lane*/, int i, float out[4]) {
     plane.row(taps, axis_tap(scale_y, i, in_h), out);
+#ifdef UNMORE_L1_PREFETCH
+    // Pull the source rows of the NEXT output row into L1 now (one 128-byte line per lane), so
+    // its taps hit L1 (~40 cycles) instead of waiting a full L2 round trip (~300 cycles).
+    if (pf_off >= 0) {
+      float src = __fmaf_rn(scale_y, (float)i + 1.5f, -0.5f);
+      int yn = (int)fmaxf(src, 0.f);
+      yn = min(yn, in_h - 1);
+      const float* q = plane.origin + (yn * plane.stride + pf_off);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+      if (yn + 1 < in_h) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + plane.stride));
+    }
+#endif
   }
 };
 
@@ -74,9 +90,39 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
   float fA = 0.f, fAg = 0.f, fB = 0.f, fBg = 0.f;
   // One output row of the 127x127 region: cur = S[i][.], nxt = S[i+1][.].
   auto process = [&](const float (&cur)[4], const float (&nxt)[4], int i) {
-    const float right = __shfl_down_sync(kFullMask, cur[0], 1);
-    if (lane == 0) cols.left[i] = cur[0];
-    if (lane == 31) cols.right[i] = cur[2];
+    const float right = __shfl_down_sync(kFullMask, cur[0], 1);  // S[i][4l+4]
+    if (lane == 0) cols.left[i] = cur[0];     // column 0
+    if (lane == 31) cols.right[i] = cur[2];   // column 126
+#ifndef UNMORE_NO_ILP
+    // the four pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a);
+    // stage them so the MUFU latencies overlap instead of serialising pixel after pixel
+    float t[4], u[4], g[4], a[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float s = cur[c];
+      const float dxv = (c < 3 ? cur[c + 1] : right) - s;
+      const float dyv = nxt[c] - s;
+      t[c] = fmaf(dyv, dyv, dxv * dxv);
+      u[c] = -1.4426950408889634f * s;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { u[c] = ex2_approx(u[c]); g[c] = sqrt_approx(t[c]); }  // ||grad|| only feeds the averaged sums
+#pragma unroll
+    for (int c = 0; c < 4; ++c) u[c] = 1.f + u[c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] = rcp_approx(u[c]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float b = 1.f - a[c];
+      if ((c < 3) || (lane < 31)) {  // column 127 is outside the 127x127 region
+        fA += a[c];
+        fAg = fmaf(a[c], g[c], fAg);
+        fB += b;
+        fBg = fmaf(b, g[c], fBg);
+      }
+      mx = fmaxf(mx, nxt[c]);
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const float s = cur[c];
@@ -93,6 +139,7 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
       }
       mx = fmaxf(mx, nxt[c]);
     }
+#endif
   };
   // fp32 partial sums are flushed into fp64 every 8 rows (32 px per lane): keeps the
   // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
@@ -165,10 +212,11 @@ __device__ __forceinline__ int one_round(const RefineParams& p, const float* pla
   const Window win = snap_window<T>(b.x1, b.y1, b.x2, b.y2, p.W, p.H);
   if (win.empty()) return -1;  // the reference would raise on a zero-size crop; defined as "no object"
   CropRows src;
-  src.taps.init(lane, win.w());
+  src.taps.init<kBlocked>(lane, win.w());
   src.plane.init(plane, p.W, win);
   src.in_h = win.h();
   src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
+  src.init_prefetch(lane, win.w());
   const Deltas d = boundary_terms(src, cols, lane);
   if (!(d.max_sdf > p.max_sdf_thres)) return -1;
   // signed deltas: >0 expands, <0 shrinks; expansion is ignored on sides glued to the image edge (:444-447)
@@ -212,7 +260,10 @@ __device__ __forceinline__ int one_round(const RefineParams& p, const float* pla
 
 constexpr int kRefineWarps = 8;
 
-__global__ void __launch_bounds__(kRefineWarps * 32, 3) refine_kernel(const RefineParams p) {
+#ifndef UNMORE_REFINE_MINBLOCKS
+#define UNMORE_REFINE_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) refine_kernel(const RefineParams p) {
   __shared__ BorderCols cols_all[kRefineWarps];
   const int lane = threadIdx.x & 31;
   BorderCols& cols = cols_all[threadIdx.x >> 5];
@@ -281,7 +332,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32) tiles_kernel(const TilePara
 }
 
 int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream) {
-  const int ctas = num_sms * 3;  // 24 warps/SM resident (<= 85 registers); warps pull proposals dynamically
+  const int ctas = num_sms * UNMORE_REFINE_MINBLOCKS;  // resident CTAs per SM; warps pull proposals dynamically
   refine_kernel<<<ctas, kRefineWarps * 32, 0, stream>>>(p);
   return (int)cudaGetLastError();
 }

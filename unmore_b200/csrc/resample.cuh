@@ -1,7 +1,14 @@
 // Warp-cooperative crop + bilinear resample to 128x128 ("a2", object_reasoning.py:402-410).
 //
-// Mapping: one warp per proposal; lane l owns the four contiguous output columns
-// 4l..4l+3 of every output row.  Horizontal interpolation of a source row is kept in
+// Mapping: one warp per proposal; each lane owns four output columns of every output row.
+// Two layouts, chosen per kernel from measurement (profiles/r01_column_mapping.md):
+//   kBlocked: columns 4l .. 4l+3.  A lane's eight taps fall into 2-3 sectors, and the first tap
+//             request of a row already touches every new sector of that row, so all L2 misses
+//             of a row are in flight at once.  26 sectors / request but 87% L1 hits; the
+//             fastest layout for the existence and refine kernels (-20% / -9% time vs strided).
+//   kStrided: columns l, l+32, l+64, l+96.  4.6 sectors / request (3x less L1 work) and a
+//             __ballot_sync yields one packed mask word per column group, which is what the
+//             mask-building kernels (center reasoning, scoring) want.  Horizontal interpolation of a source row is kept in
 // registers and reused while consecutive output rows hit the same source rows (always
 // the case when the crop is smaller than 128 px high), so an up-sampled crop costs
 // in_h * 8 loads per lane instead of 128 * 16.
@@ -10,16 +17,24 @@
 
 namespace unmore {
 
-// Column taps of this lane for the current window (shared by all channels).
+enum ColLayout { kBlocked = 0, kStrided = 1 };
+
+template <int LAYOUT>
+__device__ __forceinline__ int lane_column(int lane, int c) {
+  return LAYOUT == kStrided ? lane + 32 * c : 4 * lane + c;
+}
+
+// Column taps of this lane for the current window, shared by all channels.
 struct ColTaps {
   int x0[4];
   bool two[4];  // second tap is x0+1 (false only on the clamped right edge, where it repeats x0)
   float w0[4], w1[4];
+  template <int LAYOUT>
   __device__ __forceinline__ void init(int lane, int in_w) {
     const float scale = __fdiv_rn((float)in_w, (float)kCrop);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      AxisTap t = axis_tap(scale, 4 * lane + c, in_w);
+      AxisTap t = axis_tap(scale, lane_column<LAYOUT>(lane, c), in_w);
       x0[c] = t.i0; two[c] = t.i1 != t.i0; w0[c] = t.l0; w1[c] = t.l1;
     }
   }
@@ -50,7 +65,7 @@ struct PlaneRows {
       out[c] = lerp_h(v0, v1, t.w0[c], t.w1[c]);
     }
   }
-  // S[i][4l..4l+3] for the output row whose vertical tap is `v`
+  // S[i][lane_column(lane, c)], c = 0..3, for the output row whose vertical tap is `v`
   __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[4]) {
     if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
       if (v.i0 == cy1) {

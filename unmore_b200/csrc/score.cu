@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
   // ---- 1. resample the four channels; warp w owns rows 16w .. 16w+15
   {
     ColTaps taps;
-    taps.init(lane, win.w());
+    taps.init<kStrided>(lane, win.w());
     const size_t plane_sz = (size_t)p.H * p.W;
     const float* base = p.fields + (size_t)img * p.C * plane_sz;
     PlaneRows ps, p0, p1, pe;
@@ -80,21 +80,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
       p0.row(taps, v, a);
       p1.row(taps, v, b);
       pe.row(taps, v, e);
-      uint32_t nc = 0, nb = 0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float sq = __fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c]));  // torch.norm order
         cmax = fmaxf(cmax, sq);
         bmax = fmaxf(bmax, s[c]);
-        nc |= (__fsqrt_rn(sq) > 0.5f ? 1u : 0u) << c;
-        nb |= (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD ? 1u : 0u) << c;
+        // columns 32c .. 32c+31 of row i, LSB = lowest column
+        const uint32_t wc = __ballot_sync(kFullMask, sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
+        const uint32_t wb = __ballot_sync(kFullMask, s[c] > UNMORE_SIGMOID_HALF_THRESHOLD);
+        if (lane == 0) { sm.cmask[i][c] = wc; sm.bmask[i][c] = wb; }
       }
       esum += (double)((e[0] + e[1]) + (e[2] + e[3]));
-      uint32_t wc = nc, wb = nb;
-      wc |= __shfl_down_sync(kFullMask, wc, 1) << 4;  wb |= __shfl_down_sync(kFullMask, wb, 1) << 4;
-      wc |= __shfl_down_sync(kFullMask, wc, 2) << 8;  wb |= __shfl_down_sync(kFullMask, wb, 2) << 8;
-      wc |= __shfl_down_sync(kFullMask, wc, 4) << 16; wb |= __shfl_down_sync(kFullMask, wb, 4) << 16;
-      if ((lane & 7) == 0) { sm.cmask[i][lane >> 3] = wc; sm.bmask[i][lane >> 3] = wb; }
     }
     esum = warp_sum(esum);
     cmax = warp_max(cmax);
