@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-sample-proposals", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
 
 
@@ -187,13 +188,17 @@ def main():
     t_gen = time.time() - t_gen
 
     pipe = ReasoningPipeline(dev)
+    sat_buf = torch.empty((n_img, 2, H + 1, W + 1), dtype=torch.float64, device=dev)
 
     def step(collect_stats=None):
         rows = []
+        # north-star op (a): summed-area tables of the existence / boundary-distance fields for the
+        # whole batch in one HBM-streaming launch; the chunks below read their slices
+        sat = pipe.build_sat(fields, out=sat_buf)
         for c0 in range(0, n_img, chunk):
             c1 = min(c0 + chunk, n_img)
             st = {} if collect_stats is not None else None
-            r = pipe.run_chunk(fields[c0:c1], proposals[c0:c1], stats=st)
+            r = pipe.run_chunk(fields[c0:c1], proposals[c0:c1], stats=st, sat=sat[c0:c1])
             rows.append(pack_detections(image_ids[c0:c1], r["bbox"], r["keep_counts"], r["out"][:, :, 0].float()))
             if collect_stats is not None:
                 collect_stats["proposal_rounds"] = collect_stats.get("proposal_rounds", 0) + int(st["refine_rounds"].sum())
@@ -247,7 +252,7 @@ def main():
         "unmore_boundary_refine": n_img * px * 4 + work["refine_in"] * (32 + 16 + 4 + 4),
         "unmore_center_reasoning": n_img * px * 12 + work["center_in"] * (32 + 8 + 4 + 128),
         "unmore_existence_scores": n_img * px * 4 + work["exist_in"] * (32 + 4),
-        "unmore_sat_build": n_img * 2 * (px * 4 + (H + 1) * (W + 1) * 8),
+        "unmore_sat_build_fields": n_img * 2 * (px * 4 + (H + 1) * (W + 1) * 8),
         "unmore_score_and_rasterise": n_img * px * 16 + work["detections"] * (H * ((W + 31) // 32) * 4),
     }
     kernels = {}
@@ -336,6 +341,41 @@ def main():
         e2e = {"value": world * n_img / dt, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "host_pool_images": pool, "ms_per_step": dt * 1e3}
 
+    # ---- configs[2] side measurement (outside the step): HBM-streaming mask bit-pack and mask-IoU NMS
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        del sat_buf
+        torch.cuda.empty_cache()
+        K = 4096
+        g = torch.Generator(device=dev).manual_seed(0)
+        dense = torch.zeros((K, H, W), dtype=torch.uint8, device=dev)
+        cx = torch.rand(K, generator=g, device=dev) * W; cy = torch.rand(K, generator=g, device=dev) * H
+        rx = 20 + torch.rand(K, generator=g, device=dev) * 120; ry = 20 + torch.rand(K, generator=g, device=dev) * 120
+        ys = torch.arange(H, device=dev).view(1, H, 1); xs = torch.arange(W, device=dev).view(1, 1, W)
+        for k0 in range(0, K, 256):
+            sl = slice(k0, k0 + 256)
+            dense[sl] = ((((ys - cy[sl].view(-1, 1, 1)) / ry[sl].view(-1, 1, 1)) ** 2 +
+                          ((xs - cx[sl].view(-1, 1, 1)) / rx[sl].view(-1, 1, 1)) ** 2) < 1).to(torch.uint8)
+        msc = torch.rand(K, generator=g, device=dev)
+
+        def timed(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            return best
+        t_pack = timed(lambda: ops.mask_pack(dense))
+        packed = ops.mask_pack(dense)
+        pack_bytes = K * H * W + K * H * ((W + 31) // 32) * 4
+        t_nms = timed(lambda: ops.mask_nms(packed, W, msc, 0.5), reps=3)
+        kept = int(ops.mask_nms(packed, W, msc, 0.5).numel())
+        extras = {"mask_pack": {"masks": K, "ms": t_pack, "achieved_gbs": pack_bytes / t_pack / 1e6,
+                                "frac": pack_bytes / t_pack / 1e6 / hbm_peak, "bound": "hbm"},
+                  "mask_nms": {"masks": K, "ms": t_nms, "kept": kept, "note": "stats + rank sort + bit-matrix + greedy scan"}}
+        del dense, packed
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = cpu_sample(args.cpu_sample_proposals, n_prop)
@@ -350,7 +390,7 @@ def main():
                            "input_generation_s": round(t_gen, 1)},
                 "proposals_per_sec": images_per_s * n_prop, "detections": int(out.shape[0]),
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
-                "stage_ms_per_step": per_step, "e2e": e2e, "cpu_baseline": cpu_baseline}
+                "stage_ms_per_step": per_step, "e2e": e2e, "cpu_baseline": cpu_baseline, "extras": extras}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -144,6 +144,13 @@ int unmore_final_scores(const float* scores, const float* tight, const int* area
  * in [n_planes, H, W] fp32 -> out [n_planes, H+1, W+1] fp64, out[y][x] = sum in[:y, :x]. W <= 2048. */
 int unmore_sat_build(const float* in, int n_planes, int H, int W, double* out, unmore_stream_t stream);
 
+/* Same tables built in place from a field stack [n_img, C, H, W]: output plane (i, k) is channel
+ * channels_host[k] of image i; out [n_img, n_channels, H+1, W+1] fp64.  channels_host is a HOST
+ * array of 1..4 channel indices (north-star: existence and boundary-distance fields). */
+int unmore_sat_build_fields(const float* fields, int n_img, int C, int H, int W,
+                            const int* channels_host, int n_channels, double* out,
+                            unmore_stream_t stream);
+
 /* O(1) box sums from a table built over [n_img, planes_per_img, H, W]: the window is snapped
  * like the crops (floor x1,y1 / ceil x2,y2, object_reasoning.py:502).  sums_out / means_out
  * (nullable) [n_img, cap] fp64. */

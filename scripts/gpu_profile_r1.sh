@@ -2,7 +2,7 @@
 # Round-1 profiling pass (run under gpurun): plain run first, then the ncu launch list and one
 # --set full capture per hot kernel.  Outputs land in gpurun_out/.
 set -uo pipefail
-ARGS="--images 250 --chunk 250 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+ARGS="--images 250 --chunk 250 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-extras"
 mkdir -p gpurun_out
 python bench.py $ARGS > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py $ARGS > gpurun_out/ncu_launches.log 2>&1

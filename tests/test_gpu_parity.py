@@ -284,6 +284,12 @@ def test_sat_and_box_sums(dev, ops, shape):
     got = ops.sat_build(f.to(dev)).cpu()
     assert got.shape == ref.shape
     assert torch.allclose(got, ref, rtol=1e-12, atol=1e-9)
+    # in-place build from a [n_img, C, H, W] stack: planes (i, k) = channel (3, 0)[k] of image i
+    if shape[0] >= 2:
+        stack = torch.rand((shape[0], 4) + tuple(shape[1:]), generator=g)
+        got2 = ops.sat_build_fields(stack.to(dev), [3, 0]).cpu()
+        assert torch.allclose(got2[:, 0], O.sat_build(stack[:, 3]), rtol=1e-12, atol=1e-9)
+        assert torch.allclose(got2[:, 1], O.sat_build(stack[:, 0]), rtol=1e-12, atol=1e-9)
     H, W = shape[1:]
     boxes = torch.rand((shape[0], 50, 4), generator=g, dtype=torch.float64)
     boxes[..., 0] *= W / 2; boxes[..., 1] *= H / 2

@@ -30,6 +30,7 @@ SIGNATURES = {
     "unmore_score_and_rasterise": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
     "unmore_final_scores": [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p],
     "unmore_sat_build": [_p, _i, _i, _i, _p, _p],
+    "unmore_sat_build_fields": [_p, _i, _i, _i, _i, _p, _i, _p, _p],
     "unmore_box_sums": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
     "unmore_mask_pack": [_p, C.c_size_t, _i, _i, _p, _p],
     "unmore_mask_stats": [_p, _i, _i, _i, _p, _p, _p],

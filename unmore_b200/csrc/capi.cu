@@ -238,7 +238,19 @@ int unmore_sat_build(const float* in, int n_planes, int H, int W, double* out, u
   if (n_planes < 0 || H <= 0 || W <= 0 || (n_planes > 0 && (!in || !out)))
     return fail(UNMORE_E_INVALID, "unmore_sat_build: bad argument");
   if (W > 2048) return fail(UNMORE_E_CAPACITY, "unmore_sat_build: W %d > 2048", W);
-  return cuda_fail(launch_sat(in, out, n_planes, H, W, (cudaStream_t)stream), "sat_kernel");
+  return cuda_fail(launch_sat(in, out, n_planes, H, W, 0, nullptr, 0, (cudaStream_t)stream), "sat_kernel");
+}
+
+int unmore_sat_build_fields(const float* fields, int n_img, int C, int H, int W, const int* channels_host, int n_channels,
+                            double* out, unmore_stream_t stream) {
+  if (int e = check_fields(fields, n_img, C, H, W)) return e;
+  if (!out || !channels_host || n_channels < 1 || n_channels > 4)
+    return fail(UNMORE_E_INVALID, "unmore_sat_build_fields: bad argument (1..4 channels)");
+  for (int i = 0; i < n_channels; ++i)
+    if (channels_host[i] < 0 || channels_host[i] >= C) return fail(UNMORE_E_INVALID, "unmore_sat_build_fields: channel out of range");
+  if (W > 2048) return fail(UNMORE_E_CAPACITY, "unmore_sat_build_fields: W %d > 2048", W);
+  return cuda_fail(launch_sat(fields, out, n_img * n_channels, H, W, C, channels_host, n_channels, (cudaStream_t)stream),
+                   "sat_kernel");
 }
 
 int unmore_box_sums(const double* sat, int n_img, int planes_per_img, int plane, int H, int W, const void* boxes,

@@ -19,14 +19,20 @@ constexpr int kSatWarps = 4;
 
 __device__ __forceinline__ double shfl_up_d(double v, int o) { return __shfl_up_sync(kFullMask, v, o); }
 
+// Plane p of the output is channel sel.ch[p % sel.n] of image p / sel.n of a [n_img, C, H, W] stack
+// (sel.n == 0: `in` is a dense [n_planes, H, W] tensor), so the tables are built in place from
+// the field stack without a gather copy.
+struct PlaneSel { int n, C, ch[4]; };
+
 template <int STEPS>
 __global__ void __launch_bounds__(kSatWarps * 32) sat_kernel(const float* __restrict__ in, double* __restrict__ out,
-                                                              int n_planes, int H, int W) {
+                                                              int n_planes, int H, int W, const PlaneSel sel) {
   __shared__ double stage[kSatWarps][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int plane = blockIdx.x * kSatWarps + warp;
   if (plane >= n_planes) return;
-  const float* src = in + (size_t)plane * H * W;
+  const size_t src_plane = sel.n ? (size_t)(plane / sel.n) * sel.C + sel.ch[plane % sel.n] : (size_t)plane;
+  const float* src = in + src_plane * H * W;
   double* dst = out + (size_t)plane * (H + 1) * (W + 1);
   const int OW = W + 1;
   for (int x = lane; x < OW; x += 32) dst[x] = 0.0;  // row 0
@@ -79,13 +85,17 @@ __global__ void __launch_bounds__(kSatWarps * 32) sat_kernel(const float* __rest
   }
 }
 
-int launch_sat(const float* in, double* out, int n_planes, int H, int W, cudaStream_t stream) {
+int launch_sat(const float* in, double* out, int n_planes, int H, int W, int C, const int* channels, int n_ch,
+               cudaStream_t stream) {
   if (n_planes <= 0) return 0;
+  PlaneSel sel{};
+  sel.n = n_ch; sel.C = C;
+  for (int i = 0; i < n_ch && i < 4; ++i) sel.ch[i] = channels[i];
   const int grid = (n_planes + kSatWarps - 1) / kSatWarps;
   const int steps = (W + 127) / 128;
-  if (steps <= 5) sat_kernel<5><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W);
-  else if (steps <= 8) sat_kernel<8><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W);
-  else if (steps <= 16) sat_kernel<16><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W);
+  if (steps <= 5) sat_kernel<5><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W, sel);
+  else if (steps <= 8) sat_kernel<8><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W, sel);
+  else if (steps <= 16) sat_kernel<16><<<grid, kSatWarps * 32, 0, stream>>>(in, out, n_planes, H, W, sel);
   else return -2;
   return (int)cudaGetLastError();
 }

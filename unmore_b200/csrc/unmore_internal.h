@@ -135,7 +135,8 @@ struct FinalParams {
 int launch_final_scores(const FinalParams& p, cudaStream_t stream);
 
 // ---- sat.cu --------------------------------------------------------------------------
-int launch_sat(const float* in, double* out, int n_planes, int H, int W, cudaStream_t stream);
+int launch_sat(const float* in, double* out, int n_planes, int H, int W, int C, const int* channels, int n_ch,
+               cudaStream_t stream);
 int launch_box_sums(const double* sat, int planes_per_img, int plane, int H, int W, const void* boxes, int boxes_f64,
                     const int* counts, int cap, int n_img, double* sums, double* means, cudaStream_t stream);
 

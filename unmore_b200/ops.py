@@ -65,7 +65,7 @@ LAUNCHES = 0  # kernels launched through the C ABI since import (gpu_launches in
 _KERNELS = {"unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
             "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
             "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_box_nms_matrix": 3,
-            "unmore_score_and_rasterise": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_box_sums": 1,
+            "unmore_score_and_rasterise": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
             "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3}
 
 
@@ -290,6 +290,19 @@ def sat_build(planes: torch.Tensor) -> torch.Tensor:
     n = p.numel() // (H * W) if H * W else 0
     out = torch.empty(p.shape[:-2] + (H + 1, W + 1), dtype=torch.float64, device=p.device)
     _call("unmore_sat_build", p.data_ptr(), n, H, W, out.data_ptr(), _stream())
+    return out
+
+
+def sat_build_fields(fields: torch.Tensor, channels, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Tables of selected channels straight from the field stack: [n_img, C, H, W] fp32 ->
+    [n_img, len(channels), H+1, W+1] fp64 (no gather copy)."""
+    import ctypes
+    n_img, C, H, W = _check_fields(fields)
+    ch = (ctypes.c_int * len(channels))(*[int(c) for c in channels])
+    if out is None:
+        out = torch.empty((n_img, len(channels), H + 1, W + 1), dtype=torch.float64, device=fields.device)
+    _call("unmore_sat_build_fields", fields.data_ptr(), n_img, C, H, W, ctypes.cast(ch, ctypes.c_void_p), len(channels),
+          out.data_ptr(), _stream())
     return out
 
 

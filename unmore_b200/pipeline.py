@@ -29,8 +29,14 @@ class ReasoningPipeline:
         self.with_sat = with_sat
         self.with_masks = with_masks
 
+    def build_sat(self, fields: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """north-star op (a): summed-area tables of the existence and boundary-distance fields,
+        [B, 2, H+1, W+1] fp64, built in place from the field stack."""
+        ch = self.discovery.channels
+        return ops.sat_build_fields(fields, [ch.exist, ch.sdf], out=out)
+
     def run_chunk(self, fields: torch.Tensor, proposals: torch.Tensor, counts: Optional[torch.Tensor] = None,
-                  stats: Optional[dict] = None) -> dict:
+                  stats: Optional[dict] = None, sat: Optional[torch.Tensor] = None) -> dict:
         """fields [B,4,H,W] fp32 (device), proposals [B,N,4] fp64/fp32 (device).
         Returns device tensors: ``boxes`` [B,cap,4] discovered boxes (xyxy) and ``box_counts``;
         ``out`` [B,cap,5] fp64 (score, existence, center, boundary, area_score), ``bbox`` xywh,
@@ -39,9 +45,8 @@ class ReasoningPipeline:
         ch = self.discovery.channels
         res = {}
         if self.with_sat:
-            # north-star op (a): summed-area tables of the existence and boundary-distance fields
-            planes = torch.stack([fields[:, ch.exist], fields[:, ch.sdf]], dim=1).contiguous()
-            sat = ops.sat_build(planes)
+            if sat is None:
+                sat = self.build_sat(fields)
             res["exist_box_mean"] = ops.box_sums(sat, 0, proposals, counts)[1]
             res["sdf_box_mean"] = ops.box_sums(sat, 1, proposals, counts)[1]
         kb, kc = self.discovery.discover_batch(fields, proposals, counts, stats=stats)
