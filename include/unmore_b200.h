@@ -53,12 +53,20 @@ int unmore_existence_scores(const float* fields, int n_img, int C, int H, int W,
  * center_field_to_anti_center_map (object_reasoning.py:360-377) fused.
  * max_values_out [n_img, cap] fp64: amax of the masked anti-center map;
  * argmax_out [n_img, cap] int32: -1 if the proposal passes (max <= thr), else yc*128+xc;
- * splits_out [n_img, cap, 4, 4] fp64 (nullable): left/right/top/bottom boxes of failing rows. */
+ * splits_out [n_img, cap, 4, 4] fp64 (nullable): left/right/top/bottom boxes of failing rows.
+ * --analyze_cc (:561-572, separate_connected_components :207-256 + enlarge_proposals :259-291),
+ * all three NULL when off: cc_counts_out [n_img, cap] u8 = number of component boxes emitted
+ * for a PASSING proposal whose un-eroded union mask has >= 2 8-connected components (else 0);
+ * cc_boxes_out [n_img, cap, unmore_cc_cap(), 4] fp64 the enlarged (x1.5, int-truncated, clipped
+ * to W/H) component boxes in scipy label order; *cc_overflow is incremented for every proposal
+ * with more components than unmore_cc_cap() (the extra ones are dropped — callers must check). */
 int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W, int ch_sdf,
                             int ch_center_row, int ch_center_col, const void* boxes, int boxes_f64,
                             const int* counts, int cap, double center_score_max_thres,
-                            double* max_values_out, int* argmax_out, double* splits_out, void* ws,
-                            unmore_stream_t stream);
+                            double* max_values_out, int* argmax_out, double* splits_out,
+                            unsigned char* cc_counts_out, double* cc_boxes_out, int* cc_overflow,
+                            void* ws, unmore_stream_t stream);
+int unmore_cc_cap(void);
 
 /* boundary_reasoning — object_reasoning.py:582-612: up to n_round rounds of
  * filter_small_proposal (:293-299) + optimize_one_image_single_round (:379-487), one warp per
@@ -83,13 +91,16 @@ int unmore_update_bbox_from_tiles(const float* tiles, int M, float* deltas_out, 
 /* Order-preserving selection (the boolean-mask indexing of the reference, e.g.
  * object_reasoning.py:422-426, 541-542, 630, 656).  For every image, entries e < count whose
  * predicate holds are copied in order to out [n_img, cap_out, 4]; each entry carries `group`
- * consecutive boxes (4 for the split lists).  mode: 0 pred=u8 flags; 1 pred=fp32 >= thr;
- * 2 pred=fp32 == thr; 3 pred=int32 >= 0; 4 pred=int32 < 0.  append != 0 appends after the
- * counts_out rows already present (torch.cat of two lists, :644).  index_out (nullable)
- * [n_img, cap_out] receives the source entry index of each output row. */
+ * consecutive boxes (4 for the split lists), or group_counts[e] <= group of them when
+ * group_counts (nullable, u8 [n_img, cap_in]) is given.  mode: 0 pred=u8 flags; 1 pred=fp32 >= thr;
+ * 2 pred=fp32 == thr; 3 pred=int32 >= 0; 4 pred=int32 < 0; 5 pred=u8 != 0.  append != 0 appends
+ * after the counts_out rows already present (torch.cat of two lists, :571, :644).  index_out
+ * (nullable) [n_img, cap_out] receives the source entry index of each output row; *overflow
+ * (nullable) is incremented for every image whose rows did not fit cap_out. */
 int unmore_compact_boxes(const void* in, int in_f64, const int* counts_in, int cap_in, int group,
                          int mode, const void* pred, float thr, void* out, int out_f64, int cap_out,
-                         int* counts_out, int append, int* index_out, int n_img,
+                         int* counts_out, int append, int* index_out,
+                         const unsigned char* group_counts, int* overflow, int n_img,
                          unmore_stream_t stream);
 
 /* torchvision.ops.nms semantics — object_reasoning.py:661, object_scoring.py:238.
@@ -105,6 +116,13 @@ int unmore_box_nms(const float* boxes, const float* scores, const int* counts, i
  * erosions with a kernel_size x kernel_size ones kernel and zero border.  out: u8 {0,1}. */
 int unmore_batch_erode(const unsigned char* masks, int B, int H, int W, int kernel_size, int num_round,
                        unsigned char* out, unmore_stream_t stream);
+
+/* separate_connected_components — object_reasoning.py:207-256 on [B, 128, 128] u8 masks (non-zero
+ * = set): 8-connected labelling in scipy.ndimage.label order.  counts_out [B] = number of
+ * components; boxes_out [B, unmore_cc_cap(), 4] int32 = [x_start, y_start, x_stop, y_stop] of the
+ * first unmore_cc_cap() components. */
+int unmore_connected_components(const unsigned char* masks, int B, int H, int W, int* counts_out,
+                                int* boxes_out, unmore_stream_t stream);
 
 /* center_field_to_anti_center_map — object_reasoning.py:360-377: vote_maps [B, 2, H, W] fp32 ->
  * out [B, H, W] fp64 (5x5 normalised "points-at-me" correlation, zero padding, / 24). */

@@ -200,6 +200,59 @@ def gen_scene(od, index, n_prop, tag, n_round=50):
     return out
 
 
+def gen_scene_cc(od):
+    """center_reasoning and the whole discovery loop body with --analyze_cc (README.md:176)."""
+    import torchvision
+    H, W = 480, 640
+    out = {}
+    od.height, od.width = H, W
+    od.args.analyze_cc = True
+    od.args.n_round = 50
+    try:
+        done = []
+        for index, n_prop in [(0, 512), (4, 300), (8, 200), (12, 300), (16, 300)]:
+            if len(done) == 3:
+                break
+            img = synth.make_fields(index, H, W)
+            props = torch.tensor(synth.make_proposals(index, n_prop, H, W))
+            ex = _quiet(od.existence_checking, img, props)["existence_scores"]
+            p1 = props[ex >= od.args.class_score_thres]
+            try:
+                cr = _quiet(od.center_reasoning, img, p1)
+            except AttributeError as e:  # the reference crashes when nothing fails singularity (:571)
+                print(f"[cc] image {index}: reference crashed ({e}); skipped")
+                continue
+            done.append(index)
+            out[f"i{index}_n_prop"] = n_prop
+            out[f"i{index}_pass1"] = cr["proposals_pass_singularity"].numpy()
+            out[f"i{index}_split"] = cr["splited_new_proposals"].numpy()
+            print(f"[cc] image {index}: {len(p1)} -> pass {len(out[f'i{index}_pass1'])}, split+cc {len(out[f'i{index}_split'])}")
+        out["indices"] = np.array(done)
+        # full loop body for image 0 (the second center_reasoning must see a failing split too)
+        index, n_prop = 0, 512
+        img = synth.make_fields(index, H, W)
+        od.test_dataset = rh._OneImageDataset([img], [index])
+        od.result_folder = tempfile.mkdtemp()
+        import object_reasoning as ref_or
+        captured = {}
+        orig_dump = ref_or.json.dump
+        orig_gen = od.generate_random_proposal
+        ref_or.json.dump = lambda obj, f, *a, **k: (captured.__setitem__("results", obj), f.write("{}"))
+        od.generate_random_proposal = lambda height, width: synth.make_proposals(index, n_prop, height, width)
+        try:
+            _quiet(od.main_object_discovery)
+        finally:
+            ref_or.json.dump = orig_dump
+            del od.generate_random_proposal
+        out["disc_index"], out["disc_n_prop"] = index, n_prop
+        out["disc"] = np.asarray(captured["results"].get(index, np.zeros((0, 4), np.float32)), np.float32).reshape(-1, 4)
+        print(f"[cc] discovery with analyze_cc: {len(out['disc'])} boxes")
+    finally:
+        od.args.analyze_cc = False
+    np.savez_compressed(os.path.join(GOLD, "scene_cc.npz"), **out)
+    print("scene_cc.npz written")
+
+
 def gen_main_loop(od):
     """main_object_discovery (object_reasoning.py:615-665) over a 3-image in-memory dataset,
     results_dict captured at json.dump; then post_process.py's __main__ on scored output."""
@@ -270,7 +323,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     od = rh.make_discovery(480, 640)
-    which = sys.argv[1:] or ["units", "scene_a", "scene_b", "main"]
+    which = sys.argv[1:] or ["units", "scene_a", "scene_b", "main", "scene_cc"]
     if "units" in which:
         gen_units(od)
     if "scene_a" in which:
@@ -279,6 +332,8 @@ def main():
         gen_scene(od, index=5, n_prop=160, tag="b", n_round=50)
     if "main" in which:
         gen_main_loop(od)
+    if "scene_cc" in which:
+        gen_scene_cc(od)
 
 
 if __name__ == "__main__":

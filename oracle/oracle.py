@@ -205,7 +205,45 @@ def center_field_to_anti_center_map(vote_maps: torch.Tensor, kernel_size: int = 
 
 
 # --------------------------------------------------------------------------------------
-# a7: center_reasoning (object_reasoning.py:525-580), analyze_cc=False
+# a8: separate_connected_components (object_reasoning.py:207-256), enlarge_proposals (:259-291)
+# --------------------------------------------------------------------------------------
+def separate_connected_components(binary_masks: torch.Tensor):
+    """8-connected labelling (scipy.ndimage.label, structure = ones(3,3)); a mask with exactly one
+    component is "single"; otherwise every component's bbox [x_start, y_start, x_stop, y_stop]
+    (slice bounds, stop exclusive) goes to "multi", in label (= raster first-pixel) order."""
+    from scipy.ndimage import find_objects, label
+    single, multi, indicators = [], [], []
+    structure = np.ones((3, 3), dtype=int)
+    for b in range(binary_masks.shape[0]):
+        labeled, num = label(binary_masks[b].cpu().numpy(), structure)
+        boxes = []
+        for sl in find_objects(labeled.astype(np.int32)):
+            ys, xs = sl
+            boxes.append([xs.start, ys.start, xs.stop, ys.stop])
+        if num == 1:
+            single.append(boxes[0])
+            indicators.append(1)
+        else:
+            indicators.append(0)
+            multi.extend(boxes)
+    return {"single": single, "multi": multi}, indicators
+
+
+def enlarge_proposals(proposals, image_shape, ratio):
+    """Scale about the centre, int() truncation, clip to (height, width).  NB the reference feeds
+    128-crop coordinates here yet clips against the IMAGE size (:567) — reproduced as is."""
+    height, width = image_shape
+    out = []
+    for x1, y1, x2, y2 in proposals:
+        cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+        nw, nh = (x2 - x1) * ratio, (y2 - y1) * ratio
+        out.append([int(max(cx - nw / 2, 0)), int(max(cy - nh / 2, 0)), int(min(cx + nw / 2, width)),
+                    int(min(cy + nh / 2, height))])
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a7: center_reasoning (object_reasoning.py:525-580); analyze_cc adds a8 (:561-572)
 # --------------------------------------------------------------------------------------
 def center_reasoning(image: torch.Tensor, proposals: torch.Tensor, args, return_debug: bool = False):
     sdf_maps, center_fields = get_prediction_with_proposals(proposals, image)
@@ -242,6 +280,16 @@ def center_reasoning(image: torch.Tensor, proposals: torch.Tensor, args, return_
         splits.append([x1, y1, x2, y1 + (y2 - y1) * yr])
         splits.append([x1, y1 + (y2 - y1) * yr, x2, y2])
     out_split = torch.tensor(splits, dtype=torch.float64).reshape(-1, 4)
+    if getattr(args, "analyze_cc", False):
+        # (:561-572) components of the un-eroded union masks of the PASSING proposals; the bboxes of
+        # multi-component masks, enlarged x1.5, are appended (float32 values) to the split list.
+        # The reference crashes here when nothing failed singularity; defined as "append to empty".
+        H, W = image.shape[-2], image.shape[-1]
+        cc, _ = separate_connected_components(union[passed])
+        multi = enlarge_proposals(cc["multi"], (H, W), ratio=1.5)
+        if len(multi):
+            extra = torch.tensor(multi, dtype=torch.float32).to(torch.float64).reshape(-1, 4)
+            out_split = torch.cat((out_split, extra), dim=0)
     out = {"proposals_pass_singularity": out_pass, "splited_new_proposals": out_split}
     if return_debug:
         out.update(max_values=maxv, argmax=argmaxes, union=union, eroded=eroded, score=score)

@@ -17,7 +17,7 @@ ref = None
 bad = {}
 for it in range(n):
     ex = ops.existence_scores(fields, props)
-    mv, am, sp = ops.center_reasoning(fields, props)
+    mv, am, sp, _ = ops.center_reasoning(fields, props)
     rb, lab, _ = ops.boundary_refine(fields, rin)
     kb, kc = od.discover_batch(fields, props)
     r = sc.score_batch(fields, kb[:, :16].contiguous(), kc)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/unmore_b200.h but not exported"
-    bound = set(_lib.SIGNATURES) | {"unmore_last_error", "unmore_version", "unmore_workspace_bytes"}
+    bound = set(_lib.SIGNATURES) | {"unmore_last_error", "unmore_version", "unmore_workspace_bytes", "unmore_cc_cap"}
     assert set(names) == bound, set(names) ^ bound
     assert lib.unmore_version() >= 100
     assert lib.unmore_workspace_bytes(10) >= 4 * 12

@@ -161,6 +161,40 @@ def test_scene_scoring(golden_dir, dev, tag):
     assert np.array_equal(packed, g["score_masks_packed"]), "binary masks must be bit-exact"
 
 
+def test_analyze_cc(golden_dir, dev):
+    """a8 + :561-572 — connected components inside center reasoning, against the reference's run."""
+    from scipy.ndimage import label
+    from unmore_b200.object_reasoning import Object_Discovery, default_args
+    g = _load(golden_dir, "scene_cc.npz")
+    odc = Object_Discovery(default_args(analyze_cc=True), device=dev)
+    for index in g["indices"]:
+        index = int(index)
+        fields = synth.make_fields(index).to(dev)
+        props = torch.tensor(synth.make_proposals(index, int(g[f"i{index}_n_prop"])))
+        ex = odc.existence_checking(fields, props)["existence_scores"]
+        cr = odc.center_reasoning(fields, props[ex >= 0.1])
+        assert np.array_equal(cr["proposals_pass_singularity"].cpu().numpy(), g[f"i{index}_pass1"])
+        assert np.array_equal(cr["splited_new_proposals"].cpu().numpy(), g[f"i{index}_split"])
+    idx, n_prop = int(g["disc_index"]), int(g["disc_n_prop"])
+    det = odc.discover_image(synth.make_fields(idx).to(dev), synth.make_proposals(idx, n_prop))
+    assert_boxes_close(det, g["disc"], "discovery with analyze_cc")
+    # stand-alone labelling op against scipy on noisy masks (many small components, diagonal links)
+    rng = np.random.default_rng(3)
+    masks = (rng.random((6, 128, 128)) < 0.0005).astype(np.uint8)   # a few isolated pixels each
+    masks[0, 20:60, 30:90] = 1; masks[0, 70:100, 10:40] = 1
+    masks[1] = 0                                                     # empty: neither single nor multi
+    masks[2] = np.eye(128, dtype=np.uint8); masks[2, 5, 100] = 1     # diagonal chain is ONE 8-connected component
+    masks[3, 64, :] = 1; masks[3, :, 64] = 1                         # cross: single
+    for k in range(10):                                              # snake: long propagation path
+        masks[4, 10 + 6 * k, 5:120] = 1
+        masks[4, 10 + 6 * k:16 + 6 * k, 119 if k % 2 == 0 else 5] = 1
+    assert all(label(m, np.ones((3, 3), int))[1] <= 16 for m in masks)
+    comb, ind = Object_Discovery.separate_connected_components(torch.tensor(masks, device=dev))
+    ref, ref_ind = O.separate_connected_components(torch.tensor(masks))
+    assert ind == ref_ind and comb["single"] == ref["single"] and comb["multi"] == ref["multi"]
+    assert Object_Discovery.enlarge_proposals(ref["multi"], (480, 640), 1.5) == O.enlarge_proposals(ref["multi"], (480, 640), 1.5)
+
+
 def test_main_loop_and_post_process(golden_dir, dev, od):
     from unmore_b200.object_scoring import Object_Scoring
     from unmore_b200.post_process import select_annotations

@@ -179,3 +179,26 @@ def test_main_loop_and_post_process(golden_dir):
     assert np.array_equal(np.arange(len(keep)), g["pp_ids"])
     assert np.array_equal(np.array(anns["area_score"])[keep], g["pp_score"])
     assert np.array_equal(np.array(anns["image_id"])[keep], g["pp_image_id"])
+
+
+def test_analyze_cc_center_reasoning(golden_dir):
+    """--analyze_cc (object_reasoning.py:561-572): component boxes of passing multi-component masks
+    follow the split boxes; pinned on the scenes where the reference itself does not crash."""
+    g = _load(golden_dir, "scene_cc.npz")
+    args = O.make_args(analyze_cc=True)
+    for index in g["indices"]:
+        index = int(index)
+        img = synth.make_fields(index)
+        props = torch.tensor(synth.make_proposals(index, int(g[f"i{index}_n_prop"])))
+        ex = O.existence_checking(img, props)["existence_scores"]
+        cr = O.center_reasoning(img, props[ex >= args.class_score_thres], args)
+        assert np.array_equal(cr["proposals_pass_singularity"].numpy(), g[f"i{index}_pass1"])
+        assert np.array_equal(cr["splited_new_proposals"].numpy(), g[f"i{index}_split"])
+
+
+@pytest.mark.slow
+def test_analyze_cc_discovery(golden_dir):
+    g = _load(golden_dir, "scene_cc.npz")
+    idx, n_prop = int(g["disc_index"]), int(g["disc_n_prop"])
+    det = O.discover_image(synth.make_fields(idx), synth.make_proposals(idx, n_prop), O.make_args(analyze_cc=True))
+    assert np.array_equal(det.view(np.int32), g["disc"].view(np.int32))

@@ -19,12 +19,13 @@ _d = C.c_double
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
     "unmore_existence_scores": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
-    "unmore_center_reasoning": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p],
+    "unmore_center_reasoning": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p],
     "unmore_boundary_refine": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p, _p, _p],
     "unmore_update_bbox_from_tiles": [_p, _i, _p, _p, _p],
-    "unmore_compact_boxes": [_p, _i, _p, _i, _i, _i, _p, _f, _p, _i, _i, _p, _i, _p, _i, _p],
+    "unmore_compact_boxes": [_p, _i, _p, _i, _i, _i, _p, _f, _p, _i, _i, _p, _i, _p, _p, _p, _i, _p],
     "unmore_box_nms": [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p],
     "unmore_batch_erode": [_p, _i, _i, _i, _i, _i, _p, _p],
+    "unmore_connected_components": [_p, _i, _i, _i, _p, _p, _p],
     "unmore_anti_center_map": [_p, _i, _i, _i, _i, _p, _p],
     "unmore_box_nms_matrix": [_p, _p, _i, _f, _p, _p, _p, _p, _p],
     "unmore_score_and_rasterise": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
@@ -58,6 +59,8 @@ def load():
     lib.unmore_version.argtypes = []
     lib.unmore_workspace_bytes.restype = C.c_size_t
     lib.unmore_workspace_bytes.argtypes = [_i]
+    lib.unmore_cc_cap.restype = _i
+    lib.unmore_cc_cap.argtypes = []
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: intended
         fn.restype = _i

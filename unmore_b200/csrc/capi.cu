@@ -102,7 +102,8 @@ int unmore_existence_scores(const float* fields, int n_img, int C, int H, int W,
 int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W, int ch_sdf, int ch_center_row,
                             int ch_center_col, const void* boxes, int boxes_f64, const int* counts, int cap,
                             double center_score_max_thres, double* max_values_out, int* argmax_out,
-                            double* splits_out, void* ws, unmore_stream_t stream) {
+                            double* splits_out, unsigned char* cc_counts_out, double* cc_boxes_out, int* cc_overflow,
+                            void* ws, unmore_stream_t stream) {
   if (int e = check_fields(fields, n_img, C, H, W)) return e;
   if (!boxes || !max_values_out || !argmax_out || !ws || cap < 0 || ch_sdf < 0 || ch_sdf >= C || ch_center_row < 0 ||
       ch_center_row >= C || ch_center_col < 0 || ch_center_col >= C)
@@ -114,6 +115,9 @@ int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W,
   p.ch_sdf = ch_sdf; p.ch_crow = ch_center_row; p.ch_ccol = ch_center_col;
   p.boxes = boxes; p.boxes_f64 = boxes_f64; p.thr = center_score_max_thres;
   p.max_values = max_values_out; p.argmax = argmax_out; p.splits = splits_out;
+  if ((cc_counts_out != nullptr) != (cc_boxes_out != nullptr) || (cc_counts_out != nullptr) != (cc_overflow != nullptr))
+    return fail(UNMORE_E_INVALID, "unmore_center_reasoning: the three analyze_cc outputs go together");
+  p.cc_counts = cc_counts_out; p.cc_boxes = cc_boxes_out; p.cc_overflow = cc_overflow;
   anti_center_filter(p.filt);
   for (int i = 0; i < 25; ++i) p.filt32[i] = (float)p.filt[i];  // exact: the table is fp32-valued
   if (int e = make_worklist(p.work, counts, n_img, cap, ws, s)) return e;
@@ -148,15 +152,19 @@ int unmore_update_bbox_from_tiles(const float* tiles, int M, float* deltas_out, 
   return cuda_fail(launch_tiles(p, (cudaStream_t)stream), "tiles_kernel");
 }
 
+int unmore_cc_cap(void) { return UNMORE_CC_CAP; }
+
 int unmore_compact_boxes(const void* in, int in_f64, const int* counts_in, int cap_in, int group, int mode,
                          const void* pred, float thr, void* out, int out_f64, int cap_out, int* counts_out,
-                         int append, int* index_out, int n_img, unmore_stream_t stream) {
-  if (!in || !pred || !out || !counts_out || cap_in < 0 || cap_out < 0 || group < 1 || mode < 0 || mode > 4 || n_img < 0)
+                         int append, int* index_out, const unsigned char* group_counts, int* overflow, int n_img,
+                         unmore_stream_t stream) {
+  if (!in || !pred || !out || !counts_out || cap_in < 0 || cap_out < 0 || group < 1 || mode < 0 || mode > 5 || n_img < 0)
     return fail(UNMORE_E_INVALID, "unmore_compact_boxes: bad argument");
   CompactParams p{};
   p.in = in; p.in_f64 = in_f64; p.counts_in = counts_in; p.cap_in = cap_in; p.group = group; p.mode = mode;
   p.pred = pred; p.thr = thr; p.out = out; p.out_f64 = out_f64; p.cap_out = cap_out; p.counts_out = counts_out;
   p.append = append; p.index_out = index_out; p.n_img = n_img;
+  p.group_counts = group_counts; p.overflow = overflow;
   return cuda_fail(launch_compact(p, (cudaStream_t)stream), "compact_kernel");
 }
 
@@ -180,6 +188,14 @@ int unmore_batch_erode(const unsigned char* masks, int B, int H, int W, int kern
     return fail(UNMORE_E_INVALID, "unmore_batch_erode: bad argument");
   if (H != kCrop || W != kCrop) return fail(UNMORE_E_CAPACITY, "unmore_batch_erode: only 128x128 crops (got %dx%d)", H, W);
   return cuda_fail(launch_erode(masks, out, B, kernel_size, num_round, (cudaStream_t)stream), "erode_kernel");
+}
+
+int unmore_connected_components(const unsigned char* masks, int B, int H, int W, int* counts_out, int* boxes_out,
+                                unmore_stream_t stream) {
+  if (B < 0 || (B > 0 && (!masks || !counts_out || !boxes_out)))
+    return fail(UNMORE_E_INVALID, "unmore_connected_components: bad argument");
+  if (H != kCrop || W != kCrop) return fail(UNMORE_E_CAPACITY, "unmore_connected_components: only 128x128 crops (got %dx%d)", H, W);
+  return cuda_fail(launch_components(masks, B, counts_out, boxes_out, (cudaStream_t)stream), "components_kernel");
 }
 
 int unmore_anti_center_map(const float* vote_maps, int B, int H, int W, int kernel_size, double* out,

@@ -15,10 +15,14 @@
 
 namespace unmore {
 
-constexpr int kCenterThreads = 512;
+#ifndef UNMORE_CENTER_THREADS
+#define UNMORE_CENTER_THREADS 512
+#endif
+constexpr int kCenterThreads = UNMORE_CENTER_THREADS;
 constexpr int kCenterWarps = kCenterThreads / 32;
 constexpr int kWinLo = 10, kWinHi = 118, kWin = kWinHi - kWinLo;  // staged window of the center field
 constexpr int kErode = 12;                                         // 3 rounds x radius 4
+constexpr int kCcCap = UNMORE_CC_CAP;                               // component boxes kept per proposal
 
 struct CenterSmem {
   float c0[kWin * kWin];
@@ -30,6 +34,9 @@ struct CenterSmem {
   int red_idx[kCenterWarps];
   float red_f[kCenterWarps];
   float bcast_f[2];
+  int bcast_i[2];
+  int cc_scan[kCenterWarps];
+  int cc_box[4][kCcCap];   // x_min, y_min, x_max, y_max per component (first kCcCap components)
 };
 
 typedef unsigned __int128 u128;
@@ -41,6 +48,81 @@ __device__ __forceinline__ void store_row(uint32_t r[4], u128 v) {
   r[0] = (uint32_t)v; r[1] = (uint32_t)(v >> 32); r[2] = (uint32_t)(v >> 64); r[3] = (uint32_t)(v >> 96);
 }
 
+// 8-connected components of a 128x128 bit mask (scipy.ndimage.label with a 3x3 structure, as
+// separate_connected_components object_reasoning.py:207-256 calls it).  Labels are the smallest flat
+// index of the component (min-propagation over the 8-neighbourhood + pointer jumping), so ranking
+// the roots in raster order reproduces scipy's numbering.  All kCenterThreads threads must call.
+// lab / rank: 16384 x u16 scratch each.  Returns the component count; box[0..3][k] receives
+// x_min, y_min, x_max, y_max of the first kCcCap components (when there are >= 1).
+__device__ int label_components(const uint32_t (*mask)[4], uint16_t* lab, uint16_t* rank, int* scan,
+                                int (*box)[kCcCap]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kPix = kCrop * kCrop, kPer = kPix / kCenterThreads;
+  auto bit = [&](int q) { return (mask[q >> 7][(q >> 5) & 3] >> (q & 31)) & 1u; };
+  for (int q = tid; q < kPix; q += kCenterThreads) lab[q] = bit(q) ? (uint16_t)q : (uint16_t)0xFFFF;
+  __syncthreads();
+  for (;;) {
+    int changed = 0;
+    for (int q = tid; q < kPix; q += kCenterThreads) {
+      const uint16_t l = lab[q];
+      if (l == 0xFFFF) continue;
+      const int r = q >> 7, c = q & 127;
+      uint16_t m = l;
+#pragma unroll
+      for (int dr = -1; dr <= 1; ++dr) {
+        const int rr = r + dr;
+        if (rr < 0 || rr >= kCrop) continue;
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int cc = c + dc;
+          if (cc < 0 || cc >= kCrop) continue;
+          const uint16_t o = lab[rr * kCrop + cc];
+          m = o < m ? o : m;            // 0xFFFF (background) never wins
+        }
+      }
+      if (m < l) { lab[q] = m; changed = 1; }
+    }
+    __syncthreads();
+    for (int q = tid; q < kPix; q += kCenterThreads) {   // pointer jumping to the current root
+      uint16_t l = lab[q];
+      if (l == 0xFFFF) continue;
+      uint16_t ll = lab[l];
+      while (ll < l) { l = ll; ll = lab[l]; }
+      lab[q] = l;
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  // rank the roots in raster order: thread t owns pixels [t*kPer, (t+1)*kPer)
+  int mine = 0;
+  for (int q = tid * kPer; q < (tid + 1) * kPer; ++q) mine += (lab[q] == (uint16_t)q) ? 1 : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) scan[warp] = incl;
+  if (tid < 4 * kCcCap) box[tid / kCcCap][tid % kCcCap] = (tid / kCcCap < 2) ? (1 << 30) : -1;
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < kCenterWarps; ++w) { if (w < warp) base += scan[w]; total += scan[w]; }
+  int rk = base + incl - mine;
+  for (int q = tid * kPer; q < (tid + 1) * kPer; ++q)
+    if (lab[q] == (uint16_t)q) rank[q] = (uint16_t)min(rk++, 0xFFFF);
+  __syncthreads();
+  for (int q = tid; q < kPix; q += kCenterThreads) {
+    const uint16_t l = lab[q];
+    if (l == 0xFFFF) continue;
+    const int k2 = rank[l];
+    if (k2 >= kCcCap) continue;
+    atomicMin(&box[0][k2], q & 127); atomicMin(&box[1][k2], q >> 7);
+    atomicMax(&box[2][k2], q & 127); atomicMax(&box[3][k2], q >> 7);
+  }
+  __syncthreads();
+  return total;
+}
+
+template <bool ANALYZE_CC>
 __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CenterSmem& sm = *reinterpret_cast<CenterSmem*>(smem_raw);
@@ -241,6 +323,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       // amax over the whole map: pixels outside the eroded mask contribute 0
       const double maxv = (best_idx >= 0 && best > 0.0) ? best : 0.0;
       const bool pass = maxv <= p.thr;
+      sm.bcast_i[0] = pass ? 1 : 0;
       p.max_values[row] = maxv;
       p.argmax[row] = pass ? -1 : best_idx;
       if (!pass && p.splits) {
@@ -254,6 +337,36 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         o[8] = x1; o[9] = y1; o[10] = x2; o[11] = ys;  // top    (:555)
         o[12] = x1; o[13] = ys; o[14] = x2; o[15] = y2;  // bottom (:556)
       }
+    }
+    // ---- 4. --analyze_cc (:561-572): 8-connected components of the un-eroded union mask of a
+    // PASSING proposal (separate_connected_components :207-256); if there are several, each
+    // component's bbox, enlarged x1.5 about its centre with int() truncation and clipped against the
+    // image size (enlarge_proposals :259-291 — the reference feeds crop coordinates there), becomes a
+    // new proposal.  Labels are the smallest flat index of the component (min-propagation over the
+    // 8-neighbourhood + pointer jumping), so component order == scipy's raster first-pixel order.
+    if constexpr (ANALYZE_CC) {
+      __syncthreads();
+      int n_comp = 0;
+      if (sm.bcast_i[0] && !win.empty()) {
+        n_comp = label_components(sm.mask, reinterpret_cast<uint16_t*>(sm.c0), reinterpret_cast<uint16_t*>(sm.c1),
+                                  sm.cc_scan, sm.cc_box);   // the staged fields are dead now: reuse their storage
+        if (n_comp >= 2) {
+          if (tid < min(n_comp, kCcCap)) {
+            // bbox = [x_start, y_start, x_stop, y_stop] (slice bounds); enlarge in Python float arithmetic
+            const double bx1 = sm.cc_box[0][tid], by1 = sm.cc_box[1][tid];
+            const double bx2 = sm.cc_box[2][tid] + 1, by2 = sm.cc_box[3][tid] + 1;
+            const double cx = (bx1 + bx2) / 2, cy = (by1 + by2) / 2;
+            const double nw = (bx2 - bx1) * 1.5, nh = (by2 - by1) * 1.5;
+            double* o = p.cc_boxes + (row * kCcCap + tid) * 4;
+            o[0] = (double)(int)fmax(cx - nw / 2, 0.0);
+            o[1] = (double)(int)fmax(cy - nh / 2, 0.0);
+            o[2] = (double)(int)fmin(cx + nw / 2, (double)p.W);
+            o[3] = (double)(int)fmin(cy + nh / 2, (double)p.H);
+          }
+          if (tid == 0 && n_comp > kCcCap) atomicAdd(p.cc_overflow, 1);
+        }
+      }
+      if (tid == 0) p.cc_counts[row] = (unsigned char)(n_comp >= 2 ? min(n_comp, kCcCap) : 0);
     }
     __syncthreads();  // s_id and shared tiles are reused by the next proposal
   }
@@ -345,14 +458,57 @@ int launch_anti_center(const float* vote, double* out, int B, int H, int W, cons
   return (int)cudaGetLastError();
 }
 
-int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
+// stand-alone separate_connected_components on [B,128,128] u8 masks: counts + raw slice boxes
+struct CcSmem {
+  uint32_t mask[kCrop][4];
+  uint16_t lab[kCrop * kCrop];
+  uint16_t rank[kCrop * kCrop];
+  int scan[kCenterWarps];
+  int box[4][kCcCap];
+};
+__global__ void __launch_bounds__(kCenterThreads) components_kernel(const unsigned char* __restrict__ masks, int B,
+                                                                    int* __restrict__ counts, int* __restrict__ boxes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CcSmem& sm = *reinterpret_cast<CcSmem*>(smem_raw);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const unsigned char* m = masks + (size_t)b * kCrop * kCrop;
+  for (int w = tid; w < kCrop * 4; w += kCenterThreads) {
+    uint32_t word = 0;
+    for (int k = 0; k < 32; ++k) word |= (m[w * 32 + k] ? 1u : 0u) << k;
+    sm.mask[w >> 2][w & 3] = word;
+  }
+  __syncthreads();
+  const int n = label_components(sm.mask, sm.lab, sm.rank, sm.scan, sm.box);
+  if (tid == 0) counts[b] = n;
+  if (tid < min(n, kCcCap)) {
+    int* o = boxes + ((size_t)b * kCcCap + tid) * 4;   // [x_start, y_start, x_stop, y_stop]
+    o[0] = sm.box[0][tid]; o[1] = sm.box[1][tid]; o[2] = sm.box[2][tid] + 1; o[3] = sm.box[3][tid] + 1;
+  }
+}
+
+int launch_components(const unsigned char* masks, int B, int* counts, int* boxes, cudaStream_t stream) {
+  if (B <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(center_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+    cudaError_t e = cudaFuncSetAttribute(components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcSmem));
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  center_kernel<<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
+  components_kernel<<<B, kCenterThreads, sizeof(CcSmem), stream>>>(masks, B, counts, boxes);
+  return (int)cudaGetLastError();
+}
+
+int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(center_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(center_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (p.cc_counts) center_kernel<true><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
+  else center_kernel<false><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -53,11 +53,13 @@ __device__ __forceinline__ bool compact_pred(const CompactParams& p, size_t e) {
     case kScoreGE: return reinterpret_cast<const float*>(p.pred)[e] >= p.thr;
     case kLabelEQ: return reinterpret_cast<const float*>(p.pred)[e] == p.thr;
     case kArgmaxGE0: return reinterpret_cast<const int*>(p.pred)[e] >= 0;
-    default: return reinterpret_cast<const int*>(p.pred)[e] < 0;
+    case kArgmaxLT0: return reinterpret_cast<const int*>(p.pred)[e] < 0;
+    default: return reinterpret_cast<const unsigned char*>(p.pred)[e] != 0;
   }
 }
 
-// One CTA per image: block-wide stable stream compaction, `group` boxes per selected entry.
+// One CTA per image: block-wide stable stream compaction; a selected entry carries `group` boxes,
+// or group_counts[e] <= group of them when the per-entry counts are given (component boxes).
 __global__ void __launch_bounds__(1024) compact_kernel(const CompactParams p) {
   __shared__ int wsum[32];
   __shared__ int carry;
@@ -71,9 +73,14 @@ __global__ void __launch_bounds__(1024) compact_kernel(const CompactParams p) {
     const int e = start + threadIdx.x;
     const size_t ge = (size_t)b * p.cap_in + e;
     const bool sel = e < n_in && compact_pred(p, ge);
-    const unsigned bal = __ballot_sync(kFullMask, sel);
-    const int within = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) wsum[warp] = __popc(bal);
+    const int mine = sel ? (p.group_counts ? (int)p.group_counts[ge] : p.group) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
       int s = wsum[lane];
@@ -85,31 +92,30 @@ __global__ void __launch_bounds__(1024) compact_kernel(const CompactParams p) {
       wsum[lane] = s;
     }
     __syncthreads();
-    const int rank = carry + (warp ? wsum[warp - 1] : 0) + within;
-    if (sel) {
-      for (int g = 0; g < p.group; ++g) {
-        const int orow = base_out + rank * p.group + g;
-        if (orow >= p.cap_out) break;
-        const size_t src = ge * p.group + g, dst = (size_t)b * p.cap_out + orow;
-        double v[4];
-        if (p.in_f64) {
-          const double4 t = reinterpret_cast<const double4*>(p.in)[src];
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-          const float4 t = reinterpret_cast<const float4*>(p.in)[src];
-          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        }
-        if (p.out_f64) reinterpret_cast<double4*>(p.out)[dst] = make_double4(v[0], v[1], v[2], v[3]);
-        else reinterpret_cast<float4*>(p.out)[dst] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
-        if (p.index_out) p.index_out[dst] = e;
+    const int first = base_out + carry + (warp ? wsum[warp - 1] : 0) + incl - mine;
+    for (int g = 0; g < mine; ++g) {
+      const int orow = first + g;
+      if (orow >= p.cap_out) break;
+      const size_t src = ge * p.group + g, dst = (size_t)b * p.cap_out + orow;
+      double v[4];
+      if (p.in_f64) {
+        const double4 t = reinterpret_cast<const double4*>(p.in)[src];
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        const float4 t = reinterpret_cast<const float4*>(p.in)[src];
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
       }
+      if (p.out_f64) reinterpret_cast<double4*>(p.out)[dst] = make_double4(v[0], v[1], v[2], v[3]);
+      else reinterpret_cast<float4*>(p.out)[dst] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+      if (p.index_out) p.index_out[dst] = e;
     }
     __syncthreads();
     if (threadIdx.x == 0) carry += wsum[31];
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    int n = base_out + carry * p.group;
+    const int n = base_out + carry;
+    if (n > p.cap_out && p.overflow) atomicAdd(p.overflow, 1);
     p.counts_out[b] = n < p.cap_out ? n : p.cap_out;
   }
 }

@@ -35,9 +35,16 @@ __device__ __forceinline__ float soft_fg(float s) {
 
 struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
   const float* tile;
+  struct Pending { float4 v; };
   __device__ __forceinline__ void row(int lane, int i, float out[4]) const {
     const float4 v = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  }
+  __device__ __forceinline__ void issue(int lane, int i, Pending& p) const {
+    p.v = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
+  }
+  __device__ __forceinline__ void finish(const Pending& p, float out[4]) const {
+    out[0] = p.v.x; out[1] = p.v.y; out[2] = p.v.z; out[3] = p.v.w;
   }
 };
 
@@ -50,6 +57,13 @@ struct CropRows {  // crop window of the boundary-distance channel, resampled on
   __device__ __forceinline__ void init_prefetch(int lane, int in_w) {
     pf_off = (32 * lane < in_w + 32) ? 32 * lane : -1;
   }
+  struct Pending { AxisTap v; int mode; PlaneRows::Raw raw; };
+  __device__ __forceinline__ void issue(int /*lane*/, int i, Pending& p) const {
+    p.v = axis_tap(scale_y, i, in_h);
+    p.mode = plane.plan(p.v);
+    plane.issue(taps, p.v, p.mode, p.raw);
+  }
+  __device__ __forceinline__ void finish(const Pending& p, float out[4]) { plane.finish(taps, p.v, p.mode, p.raw, out); }
   __device__ __forceinline__ void row(int /*lane*/, int i, float out[4]) {
     plane.row(taps, axis_tap(scale_y, i, in_h), out);
 #ifdef UNMORE_L1_PREFETCH
@@ -148,6 +162,27 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     fA = fAg = fB = fBg = 0.f;
   };
   // rows ping-pong between ra / rb so no register copies are needed
+#ifdef UNMORE_REFINE_PIPELINE
+  // software pipeline: the taps of output row i+2 are requested before row i is reduced and
+  // consumed after it, so their L1/L2 latency hides behind ~100 instructions of math
+  typename RowSrc::Pending pend;
+  src.row(lane, 1, rb);
+  src.issue(lane, 2, pend);
+  for (int i = 0; i < kCrop - 2; i += 2) {
+    process(ra, rb, i);
+    src.finish(pend, ra);                       // row i+2
+    src.issue(lane, min(i + 3, kCrop - 1), pend);
+    process(rb, ra, i + 1);
+    src.finish(pend, rb);                       // row i+3
+    if (i + 4 < kCrop) src.issue(lane, i + 4, pend);
+    if ((i & 7) == 6) flush();
+  }
+  // i = 126: ra holds row 126, rb row 127
+#pragma unroll
+  for (int c = 0; c < 4; ++c) bot[c] = ra[c];
+  process(ra, rb, kCrop - 2);
+  flush();
+#else
   for (int i = 0; i < kCrop - 2; i += 2) {
     src.row(lane, i + 1, rb);
     process(ra, rb, i);
@@ -161,6 +196,7 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
   src.row(lane, kCrop - 1, rb);
   process(ra, rb, kCrop - 2);
   flush();
+#endif
   Deltas d;
   d.max_sdf = warp_max(mx);
   const float sumA = (float)warp_sum(dA);

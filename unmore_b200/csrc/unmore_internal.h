@@ -48,6 +48,9 @@ struct ExistParams {
 int launch_existence(const ExistParams& p, int num_sms, cudaStream_t stream);
 
 // ---- center.cu -----------------------------------------------------------------------
+#ifndef UNMORE_CC_CAP
+#define UNMORE_CC_CAP 16   // connected-component boxes kept per proposal (--analyze_cc); overflow is counted
+#endif
 struct CenterParams {
   const float* fields;
   int C, H, W, ch_sdf, ch_crow, ch_ccol;
@@ -62,8 +65,13 @@ struct CenterParams {
   // filt[i*5+j] = (2-i)/sqrt((2-i)^2+(2-j)^2); channel 1 uses the transposed entry
   double filt[25];
   float filt32[25];    // the same values before the cast to double (fp32 screening pass)
+  // --analyze_cc (object_reasoning.py:561-572); all three null when off
+  unsigned char* cc_counts;  // [n_img, cap] component boxes emitted (0 unless the proposal passes with >= 2 components)
+  double* cc_boxes;          // [n_img, cap, UNMORE_CC_CAP, 4] enlarged component boxes
+  int* cc_overflow;          // incremented once per proposal with more than UNMORE_CC_CAP components
 };
 int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream);
+int launch_components(const unsigned char* masks, int B, int* counts, int* boxes, cudaStream_t stream);
 int launch_erode(const unsigned char* in, unsigned char* out, int B, int kernel_size, int num_round, cudaStream_t stream);
 int launch_anti_center(const float* vote, double* out, int B, int H, int W, const double* filt25, cudaStream_t stream);
 
@@ -76,7 +84,9 @@ struct CompactParams {
   int in_f64;
   const int* counts_in;  // nullable
   int cap_in;
-  int group;             // boxes per entry (1, or 4 for split boxes)
+  int group;             // boxes per entry (1, or 4 for split boxes); row stride of `in` when group_counts is set
+  const unsigned char* group_counts;  // nullable [n_img, cap_in]: boxes actually carried by each entry (<= group)
+  int* overflow;         // nullable: incremented per image whose output did not fit cap_out
   int mode;
   const void* pred;      // u8 flags / float scores / float labels / int argmax, [n_img, cap_in]
   float thr;

@@ -39,9 +39,6 @@ class Object_Discovery:
         for k, v in HYPER_DEFAULTS.items():
             if not hasattr(self.args, k):
                 setattr(self.args, k, v)
-        if getattr(self.args, "analyze_cc", False):
-            raise NotImplementedError("--analyze_cc (connected components, object_reasoning.py:561-572) "
-                                      "is not on the CUDA path yet (SURVEY.md §8f rank 3)")
         self.device = torch.device(device if device is not None else "cuda:0")
         if self.device.type != "cuda":
             raise RuntimeError("unmore_b200 has no CPU path; pass a CUDA device")
@@ -88,11 +85,52 @@ class Object_Discovery:
         if boxes.shape[1] == 0:
             e = torch.zeros((0, 4), dtype=torch.float64, device=self.device)
             return {"proposals_pass_singularity": e, "splited_new_proposals": e.clone()}
-        _, argmax, splits = ops.center_reasoning(self._fields(image), boxes, thr=self.args.center_score_max_thres,
-                                                 ch=self.channels)
+        cc_on = bool(getattr(self.args, "analyze_cc", False))
+        _, argmax, splits, cc = ops.center_reasoning(self._fields(image), boxes, thr=self.args.center_score_max_thres,
+                                                     ch=self.channels, analyze_cc=cc_on)
         fail = argmax[0] >= 0
-        return {"proposals_pass_singularity": boxes[0][~fail],
-                "splited_new_proposals": splits[0][fail].reshape(-1, 4)}
+        new = splits[0][fail].reshape(-1, 4)
+        if cc_on:
+            # (:561-572) enlarged component boxes of passing multi-component masks, appended after the splits
+            counts, cboxes, overflow = cc
+            if int(overflow.item()):
+                raise RuntimeError("a proposal has more connected components than unmore_cc_cap()")
+            valid = torch.arange(cboxes.shape[2], device=self.device)[None, :] < counts[0][:, None].to(torch.long)
+            new = torch.cat((new, cboxes[0][valid]), dim=0)
+        return {"proposals_pass_singularity": boxes[0][~fail], "splited_new_proposals": new}
+
+    @staticmethod
+    def separate_connected_components(binary_masks):
+        """object_reasoning.py:207-256 — ({'single': [...], 'multi': [...]}, indicators) with bboxes
+        [x_start, y_start, x_stop, y_stop]; labelling on the GPU (8-connected, scipy label order)."""
+        counts, boxes = ops.connected_components((binary_masks != 0).to(torch.uint8))
+        counts, boxes = counts.cpu().tolist(), boxes.cpu().tolist()
+        cap = len(boxes[0]) if boxes else 0
+        combined = {"single": [], "multi": []}
+        indicators = []
+        for n, bb in zip(counts, boxes):
+            if n > cap:
+                raise RuntimeError("a mask has more connected components than unmore_cc_cap()")
+            if n == 1:
+                combined["single"].append(bb[0])
+                indicators.append(1)
+            else:
+                indicators.append(0)
+                combined["multi"].extend(bb[:n])
+        return combined, indicators
+
+    @staticmethod
+    def enlarge_proposals(proposals, image_shape, ratio):
+        """object_reasoning.py:259-291 (host arithmetic on a handful of boxes; fused on the device
+        inside center_reasoning when args.analyze_cc is set)."""
+        height, width = image_shape
+        out = []
+        for x1, y1, x2, y2 in proposals:
+            cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+            nw, nh = (x2 - x1) * ratio, (y2 - y1) * ratio
+            out.append([int(max(cx - nw / 2, 0)), int(max(cy - nh / 2, 0)), int(min(cx + nw / 2, width)),
+                        int(min(cy + nh / 2, height))])
+        return out
 
     # ---- a9 ---------------------------------------------------------------------------
     def filter_small_proposal(self, proposals, labels):
@@ -170,7 +208,7 @@ class Object_Discovery:
         NMS for a batch of images, entirely on device.
 
         fields [B,4,H,W] fp32, proposals [B,N,4] fp64/fp32, counts [B] int32 or None.
-        Returns (boxes [B, 5N, 4] fp32, counts [B] int32) in the reference's output order."""
+        Returns (boxes [B, 5N (9N with --analyze_cc), 4] fp32, counts [B] int32) in the reference's output order."""
         a = self.args
         ch = self.channels
         B, N = proposals.shape[0], proposals.shape[1]
@@ -181,16 +219,27 @@ class Object_Discovery:
         ex = ops.existence_scores(fields, proposals, counts, ch=ch, ws=ws)
         p1, c1, _ = ops.compact_boxes(proposals, counts, ops.MODE_SCORE_GE, ex, thr=a.class_score_thres, out_dtype=f64)
         # Step 2: center reasoning (:634-637)
-        _, am1, sp1 = ops.center_reasoning(fields, p1, c1, thr=a.center_score_max_thres, ch=ch, ws=ws)
-        cap_out = 5 * N
+        cc_on = bool(getattr(a, "analyze_cc", False))
+        _, am1, sp1, cc = ops.center_reasoning(fields, p1, c1, thr=a.center_score_max_thres, ch=ch, ws=ws,
+                                               analyze_cc=cc_on)
+        split_cap = 8 * N if cc_on else 4 * N   # 4 split boxes per failing proposal (+ component boxes with --analyze_cc)
+        cap_out = N + split_cap
         refine_in = torch.zeros((B, cap_out, 4), dtype=f64, device=dev)
         rc = torch.zeros((B,), dtype=torch.int32, device=dev)
         ops.compact_boxes(p1, c1, ops.MODE_ARGMAX_LT0, am1, out=refine_in, counts_out=rc)
-        split, sc, _ = ops.compact_boxes(sp1, c1, ops.MODE_ARGMAX_GE0, am1, group=4, out_dtype=f64)
+        split, sc, _ = ops.compact_boxes(sp1, c1, ops.MODE_ARGMAX_GE0, am1, group=4, out_dtype=f64, cap_out=split_cap)
+        if cc_on:
+            # (:561-572) component boxes of passing multi-component masks follow the split boxes
+            cc_counts, cc_boxes, cc_over = cc
+            lost = torch.zeros((1,), dtype=torch.int32, device=dev)
+            ops.compact_boxes(cc_boxes, c1, ops.MODE_U8_NONZERO, cc_counts, group=cc_boxes.shape[2], out=split,
+                              counts_out=sc, append=True, group_counts=cc_counts, overflow=lost)
+            if int(cc_over.item()) or int(lost.item()):   # one sync per batch, only with --analyze_cc
+                raise RuntimeError("analyze_cc: component boxes exceeded unmore_cc_cap() or the split-list capacity")
         # re-check the split proposals (:639-646)
         ex2 = ops.existence_scores(fields, split, sc, ch=ch, ws=ws)
         p2, c2, _ = ops.compact_boxes(split, sc, ops.MODE_SCORE_GE, ex2, thr=a.class_score_thres, out_dtype=f64)
-        _, am2, _ = ops.center_reasoning(fields, p2, c2, thr=a.center_score_max_thres, ch=ch, ws=ws, want_splits=False)
+        _, am2, _, _ = ops.center_reasoning(fields, p2, c2, thr=a.center_score_max_thres, ch=ch, ws=ws, want_splits=False)
         ops.compact_boxes(p2, c2, ops.MODE_ARGMAX_LT0, am2, out=refine_in, counts_out=rc, append=True)
         # Step 3: boundary reasoning (:650-658)
         rb, lab, rounds = ops.boundary_refine(fields, refine_in, rc, n_round=a.n_round, apply_small_filter=True,

@@ -64,7 +64,7 @@ LAUNCHES = 0  # kernels launched through the C ABI since import (gpu_launches in
 # kernels per C-ABI call (memsets not counted); +1 when a counts prefix is built
 _KERNELS = {"unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
             "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
-            "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_box_nms_matrix": 3,
+            "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_connected_components": 1, "unmore_box_nms_matrix": 3,
             "unmore_score_and_rasterise": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
             "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3}
 
@@ -126,7 +126,9 @@ def existence_scores(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANNELS
 
 
 def center_reasoning(fields, boxes, counts=None, thr: float = 0.009, ch: Channels = DEFAULT_CHANNELS, ws=None,
-                     want_splits: bool = True):
+                     want_splits: bool = True, analyze_cc: bool = False):
+    """-> (max_values [n_img,cap] fp64, argmax [n_img,cap] int32 (-1 = passes), splits [n_img,cap,4,4] fp64 or None,
+    cc) where cc is None or (cc_counts [n_img,cap] u8, cc_boxes [n_img,cap,CC_CAP,4] fp64, overflow [1] int32)."""
     n_img, C, H, W = _check_fields(fields)
     cap, f64 = _check_boxes(boxes, n_img)
     _check_counts(counts, n_img)
@@ -135,10 +137,17 @@ def center_reasoning(fields, boxes, counts=None, thr: float = 0.009, ch: Channel
     maxv = torch.zeros((n_img, cap), dtype=torch.float64, device=dev)
     argmax = torch.full((n_img, cap), -1, dtype=torch.int32, device=dev)
     splits = torch.zeros((n_img, cap, 4, 4), dtype=torch.float64, device=dev) if want_splits else None
+    cc = None
+    if analyze_cc:
+        cc_cap = _lib.load().unmore_cc_cap()
+        cc = (torch.zeros((n_img, cap), dtype=torch.uint8, device=dev),
+              torch.zeros((n_img, cap, cc_cap, 4), dtype=torch.float64, device=dev),
+              torch.zeros((1,), dtype=torch.int32, device=dev))
     _call("unmore_center_reasoning", fields.data_ptr(), n_img, C, H, W, ch.sdf, ch.center_row, ch.center_col,
-              boxes.data_ptr(), f64, _ptr(counts), cap, float(thr), maxv.data_ptr(), argmax.data_ptr(),
-              _ptr(splits), ws.data_ptr(), _stream(), counts=counts)
-    return maxv, argmax, splits
+          boxes.data_ptr(), f64, _ptr(counts), cap, float(thr), maxv.data_ptr(), argmax.data_ptr(),
+          _ptr(splits), _ptr(cc[0]) if cc else None, _ptr(cc[1]) if cc else None, _ptr(cc[2]) if cc else None,
+          ws.data_ptr(), _stream(), counts=counts)
+    return maxv, argmax, splits, cc
 
 
 def boundary_refine(fields, boxes, counts=None, n_round: int = 50, apply_small_filter: bool = True,
@@ -171,11 +180,11 @@ def update_bbox_from_tiles(tiles: torch.Tensor):
     return deltas, mx
 
 
-MODE_FLAGS, MODE_SCORE_GE, MODE_LABEL_EQ, MODE_ARGMAX_GE0, MODE_ARGMAX_LT0 = range(5)
+MODE_FLAGS, MODE_SCORE_GE, MODE_LABEL_EQ, MODE_ARGMAX_GE0, MODE_ARGMAX_LT0, MODE_U8_NONZERO = range(6)
 
 
 def compact_boxes(inp, counts_in, mode, pred, thr=0.0, group=1, out=None, counts_out=None, cap_out=None,
-                  out_dtype=None, append=False, want_index=False):
+                  out_dtype=None, append=False, want_index=False, group_counts=None, overflow=None):
     """Stable per-image selection; returns (out [n_img, cap_out, 4], counts_out [n_img], index or None)."""
     dev = inp.device
     if group == 1:
@@ -193,7 +202,7 @@ def compact_boxes(inp, counts_in, mode, pred, thr=0.0, group=1, out=None, counts
     index = torch.full((n_img, cap_out), -1, dtype=torch.int32, device=dev) if want_index else None
     _call("unmore_compact_boxes", inp.data_ptr(), int(inp.dtype == torch.float64), _ptr(counts_in), cap_in,
               group, mode, pred.data_ptr(), float(thr), out.data_ptr(), int(out.dtype == torch.float64), cap_out,
-              counts_out.data_ptr(), int(append), _ptr(index), n_img, _stream())
+              counts_out.data_ptr(), int(append), _ptr(index), _ptr(group_counts), _ptr(overflow), n_img, _stream())
     return out, counts_out, index
 
 
@@ -237,6 +246,17 @@ def batch_erode(masks_u8: torch.Tensor, kernel_size: int = 9, num_round: int = 3
     out = torch.empty_like(m)
     _call("unmore_batch_erode", m.data_ptr(), B, H, W, int(kernel_size), int(num_round), out.data_ptr(), _stream())
     return out
+
+
+def connected_components(masks_u8: torch.Tensor):
+    """[B,128,128] u8 -> (counts [B] int32, boxes [B, CC_CAP, 4] int32 slice bounds) in scipy label order."""
+    m = masks_u8.contiguous()
+    B, H, W = m.shape
+    cap = _lib.load().unmore_cc_cap()
+    counts = torch.zeros((B,), dtype=torch.int32, device=m.device)
+    boxes = torch.zeros((B, cap, 4), dtype=torch.int32, device=m.device)
+    _call("unmore_connected_components", m.data_ptr(), B, H, W, counts.data_ptr(), boxes.data_ptr(), _stream())
+    return counts, boxes
 
 
 def anti_center_map(vote_maps: torch.Tensor, kernel_size: int = 5) -> torch.Tensor:
