@@ -183,6 +183,14 @@ int unmore_mask_pack(const unsigned char* in, size_t K, int H, int W, uint32_t* 
 int unmore_mask_stats(const uint32_t* masks, int K, int H, int W, int* areas_out, int* tight_out,
                       unmore_stream_t stream);
 
+/* binary_mask_to_rle — object_scoring.py:167-170 (pycocotools maskApi.c rleEncode): column-major
+ * run lengths of packed masks.  counts_out [K, max_runs] u32 (counts[0] = leading zeros, possibly
+ * 0); n_runs_out [K] = number of runs; a mask with more than max_runs (or 8193) runs gets only its
+ * run count written.  The compressed ASCII "counts" string is formed on the host from these
+ * (unmore_b200/rle.py, rleToString). */
+int unmore_mask_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs,
+                           uint32_t* counts_out, int* n_runs_out, unmore_stream_t stream);
+
 /* Mask-IoU NMS on packed masks (north-star op (c); no reference counterpart, oracle = dense
  * greedy restatement in torchvision's order): suppress j if popc(a&b)/(area_a+area_b-popc(a&b))
  * > thr (fp32 division of exact integers).  areas / tight from unmore_mask_stats.

@@ -553,6 +553,49 @@ def score_image(image: torch.Tensor, raw_proposals, args) -> Dict[str, np.ndarra
 
 
 # --------------------------------------------------------------------------------------
+# a16: binary_mask_to_rle (object_scoring.py:167-170) — pycocotools 2.0.7 is absent: restated from
+# the published maskApi.c (rleEncode / rleToString).  PARITY UNPINNED: no pycocotools, no RLE
+# fixture in the reference; anchored on hand-derived known answers and the decode round trip.
+# --------------------------------------------------------------------------------------
+def rle_counts(mask: np.ndarray) -> List[int]:
+    """rleEncode: column-major run lengths, counts[0] = leading zeros (possibly 0)."""
+    m = np.asarray(mask).astype(np.uint8).T.reshape(-1)   # column-major scan
+    cnts, p, c = [], 0, 0
+    for v in m:
+        if v != p:
+            cnts.append(c)
+            c, p = 0, v
+        c += 1
+    cnts.append(c)
+    return cnts
+
+
+def rle_counts_np(mask: np.ndarray) -> List[int]:
+    """Vectorised form of ``rle_counts`` for large masks."""
+    m = np.asarray(mask).astype(np.uint8).T.reshape(-1)
+    change = np.nonzero(np.diff(np.concatenate([[0], m])))[0]
+    edges = np.concatenate([[0], change, [m.size]])
+    return np.diff(edges).astype(np.int64).tolist()
+
+
+def rle_to_string(cnts) -> str:
+    """rleToString: 6 bits per ASCII char (48..111), 5 data bits + continuation, sign-extended;
+    counts from index 3 on are stored as differences to the count two places earlier."""
+    out = []
+    for i, c in enumerate(cnts):
+        x = int(c) - int(cnts[i - 2]) if i > 2 else int(c)
+        more = True
+        while more:
+            ch = x & 0x1F
+            x >>= 5
+            more = (x != -1) if (ch & 0x10) else (x != 0)
+            if more:
+                ch |= 0x20
+            out.append(chr(ch + 48))
+    return "".join(out)
+
+
+# --------------------------------------------------------------------------------------
 # a17: post_process filter (post_process.py:61-74)
 # --------------------------------------------------------------------------------------
 def post_process_filter(existence, center, boundary, args) -> np.ndarray:

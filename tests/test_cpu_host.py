@@ -73,6 +73,31 @@ def test_post_process_mirror():
     assert [a["id"] for a in sel] == [0, 1] and [a["score"] for a in sel] == [0.5, 0.7]  # thresholds are strict '<'
 
 
+def test_rle_codec_known_answers_and_round_trip():
+    """COCO RLE (a16).  pycocotools is absent, so the anchors are answers derived by hand from the
+    published maskApi.c (rleEncode / rleToString) plus the decode round trip — parity unpinned."""
+    from oracle import oracle as O
+    from unmore_b200 import rle
+    # column-major [0,1,1,1] -> counts [1,3]; all ones -> leading zero-length run
+    assert O.rle_counts(np.array([[0, 1], [1, 1]])) == [1, 3] and O.rle_to_string([1, 3]) == "13"
+    assert O.rle_counts(np.ones((2, 2))) == [0, 4] and O.rle_to_string([0, 4]) == "04"
+    assert O.rle_counts(np.zeros((3, 2))) == [6] and O.rle_to_string([6]) == "6"
+    # 5-bit groups: 31 = 0b11111 has bit 4 set, so a continuation group follows ('o' = 63+48, then '0');
+    # 32 -> low group 0 with continuation ('P' = 32+48) then '1'; third+ counts are deltas
+    assert rle.counts_to_string([31]) == "o0" and rle.counts_to_string([32]) == "P1"
+    assert rle.counts_to_string([5, 7, 9, 3]) == "579" + rle.counts_to_string([3 - 7])   # delta -4, sign-extended
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        h, w = (int(v) for v in rng.integers(1, 90, 2))
+        m = (rng.random((h, w)) < rng.random()).astype(np.uint8)
+        c = O.rle_counts(m)
+        assert c == O.rle_counts_np(m) and sum(c) == h * w
+        s = O.rle_to_string(c)
+        assert s == rle.counts_to_string(c) and rle.string_to_counts(s) == c
+        assert np.array_equal(rle.decode({"size": [h, w], "counts": s}), m)
+        assert all(48 <= ord(ch) <= 111 for ch in s)
+
+
 def test_shard_ranges_cover_everything():
     from unmore_b200.sharding import shard_indices, shard_range
     for n, w in [(5000, 8), (7, 3), (2, 4), (0, 2)]:

@@ -368,6 +368,35 @@ def test_mask_pack_and_mask_nms(dev, ops, W):
     assert np.array_equal(keep, O.mask_nms_dense(dense, scores, 0.1))
 
 
+@pytest.mark.parametrize("W", [640, 100])
+def test_rle_from_packed_masks(dev, ops, W):
+    """a16 binary_mask_to_rle: GPU run lengths + host string against the restated codec; decode
+    round trip back to the dense mask."""
+    from unmore_b200 import rle
+    H, k = 96, 40
+    dense = _random_masks(k, H, W, seed=9)
+    dense[3] = 1                                   # all ones: zero-length leading run
+    dense[4, ::2, ::2] = 1                         # many short runs
+    packed = ops.mask_pack(torch.tensor(dense, device=dev))
+    enc = rle.encode_packed(packed, W, max_runs=256)   # forces the grow-and-retry path for mask 4
+    for i in range(k):
+        c = O.rle_counts_np(dense[i])
+        assert enc[i] == {"size": [H, W], "counts": O.rle_to_string(c)}, i
+        assert np.array_equal(rle.decode(enc[i]), dense[i])
+
+
+def test_scoring_with_rle_segmentation(golden_dir, dev):
+    from unmore_b200 import rle
+    from unmore_b200.object_scoring import Object_Scoring
+    g = _load(golden_dir, "scene_a.npz")
+    fields = synth.make_fields(int(g["index"])).to(dev)
+    anns = Object_Scoring(device=dev).score_image(fields, g["discovered"].astype(np.float64).tolist(), rle=True)
+    masks = np.stack([rle.decode(a["segmentation"]) for a in anns])
+    packed = np.packbits(masks.reshape(len(anns), -1), axis=1, bitorder="little")
+    assert np.array_equal(packed, g["score_masks_packed"])
+    assert rle.scored_annotations_json(anns).startswith("[")
+
+
 # ------------------------------------------------------------------------------------------
 # full-size properties (configs[1] shapes: 480x640 fields, 4096 proposals per image)
 # ------------------------------------------------------------------------------------------

@@ -35,6 +35,7 @@ SIGNATURES = {
     "unmore_box_sums": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
     "unmore_mask_pack": [_p, C.c_size_t, _i, _i, _p, _p],
     "unmore_mask_stats": [_p, _i, _i, _i, _p, _p, _p],
+    "unmore_mask_rle_counts": [_p, _i, _i, _i, _i, _p, _p, _p],
     "unmore_mask_nms": [_p, _i, _i, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p],
 }
 

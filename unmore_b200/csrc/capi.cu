@@ -293,6 +293,14 @@ int unmore_mask_stats(const uint32_t* masks, int K, int H, int W, int* areas_out
                    "mask_stats_kernel");
 }
 
+int unmore_mask_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs, uint32_t* counts_out,
+                           int* n_runs_out, unmore_stream_t stream) {
+  if (K < 0 || H <= 0 || W <= 0 || max_runs < 1 || (K > 0 && (!masks || !counts_out || !n_runs_out)))
+    return fail(UNMORE_E_INVALID, "unmore_mask_rle_counts: bad argument");
+  return cuda_fail(launch_rle_counts(masks, K, H, W, max_runs, counts_out, n_runs_out, (cudaStream_t)stream),
+                   "rle_counts_kernel");
+}
+
 int unmore_mask_nms(const uint32_t* masks, int K, int H, int W, const float* scores, const int* areas, const int* tight,
                     float iou_threshold, int* order_ws, void* matrix_ws, int* keep_out, int* keep_count_out,
                     unmore_stream_t stream) {

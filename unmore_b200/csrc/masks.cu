@@ -200,6 +200,71 @@ __global__ void __launch_bounds__(32) greedy_scan_kernel(const unsigned long lon
   if (lane == 0) *keep_count = nk;
 }
 
+// ---- COCO run-length counts (pycocotools maskApi.c rleEncode semantics) ----------------------
+// Column-major scan (t = x*H + y); counts[0] is the length of the leading run of zeros (possibly 0),
+// then alternating one / zero runs.  One CTA per mask: each thread scans a contiguous range of t,
+// change positions are ranked with a block scan and staged in shared memory, counts are their
+// differences.  n_runs_out reports the true number of runs even when it exceeds max_runs (then
+// nothing is written for that mask and the caller falls back to a larger buffer).
+constexpr int kRleThreads = 256;
+constexpr int kRleMaxRuns = 8192;   // change positions staged in 32 KB of shared memory
+
+__global__ void __launch_bounds__(kRleThreads) rle_counts_kernel(const uint32_t* __restrict__ masks, int K, int H, int W,
+                                                                  int Wp, int max_runs, uint32_t* __restrict__ counts,
+                                                                  int* __restrict__ n_runs) {
+  __shared__ uint32_t pos[kRleMaxRuns];
+  __shared__ int wsum[kRleThreads / 32];
+  const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* m = masks + (size_t)k * H * Wp;
+  const int N = H * W;
+  const int per = (N + kRleThreads - 1) / kRleThreads;
+  const int t0 = min(tid * per, N), t1 = min(t0 + per, N);
+  auto bit = [&](int t) -> uint32_t {
+    const int x = t / H, y = t - x * H;
+    return (__ldg(m + (size_t)y * Wp + (x >> 5)) >> (x & 31)) & 1u;
+  };
+  // pass 1: count the changes in [t0, t1)
+  uint32_t prev = t0 > 0 ? bit(t0 - 1) : 0u;
+  int mine = 0;
+  {
+    uint32_t p = prev;
+    for (int t = t0; t < t1; ++t) { const uint32_t b = bit(t); mine += (b != p); p = b; }
+  }
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < kRleThreads / 32; ++w) { if (w < warp) base += wsum[w]; total += wsum[w]; }
+  const int runs = total + 1;
+  if (tid == 0) n_runs[k] = runs;
+  if (runs > max_runs || total > kRleMaxRuns) return;   // uniform
+  // pass 2: record the change positions
+  int r = base + incl - mine;
+  {
+    uint32_t p = prev;
+    for (int t = t0; t < t1; ++t) { const uint32_t b = bit(t); if (b != p) pos[r++] = (uint32_t)t; p = b; }
+  }
+  __syncthreads();
+  uint32_t* out = counts + (size_t)k * max_runs;
+  for (int j = tid; j < runs; j += kRleThreads) {
+    const uint32_t lo = j == 0 ? 0u : pos[j - 1];
+    const uint32_t hi = j == total ? (uint32_t)N : pos[j];
+    out[j] = hi - lo;
+  }
+}
+
+int launch_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs, uint32_t* counts, int* n_runs,
+                      cudaStream_t stream) {
+  if (K <= 0) return 0;
+  rle_counts_kernel<<<K, kRleThreads, 0, stream>>>(masks, K, H, W, (W + 31) >> 5, max_runs, counts, n_runs);
+  return (int)cudaGetLastError();
+}
+
 int launch_mask_stats(const uint32_t* masks, int K, int H, int Wp, int* areas, int4* tight, cudaStream_t stream) {
   if (K <= 0) return 0;
   mask_stats_kernel<<<K, 256, 0, stream>>>(masks, K, H, Wp, areas, tight);

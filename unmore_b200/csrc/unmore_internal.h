@@ -152,6 +152,8 @@ int launch_box_sums(const double* sat, int planes_per_img, int plane, int H, int
 
 // ---- masks.cu ------------------------------------------------------------------------
 int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, cudaStream_t stream);
+int launch_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs, uint32_t* counts, int* n_runs,
+                      cudaStream_t stream);
 int launch_mask_stats(const uint32_t* masks, int K, int H, int Wp, int* areas, int4* tight, cudaStream_t stream);
 int launch_matrix_nms(const uint32_t* masks, const float4* boxes, int K, int H, int Wp, const float* scores,
                       const int* areas, const int4* tight, float thr, int* order, unsigned long long* matrix,

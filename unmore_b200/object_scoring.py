@@ -63,9 +63,19 @@ class Object_Scoring:
         return dict(out=out, bbox=bbox, selected=sel, keep=keep, keep_counts=kc, masks=masks, areas=areas, tight=tight,
                     scores=scores)
 
-    def score_image(self, image, raw_proposals, image_id=0, with_masks: bool = True) -> List[dict]:
-        """Annotations of one image with the reference's keys (object_scoring.py:257-267);
-        'segmentation' holds {'size': [H, W], 'mask': uint8 [H, W]} instead of a pycocotools RLE string."""
+    @staticmethod
+    def binary_mask_to_rle(binary_mask):
+        """object_scoring.py:167-170 for one dense [H, W] mask (tensor or array): packs it, takes the
+        run lengths on the GPU and returns {'size': [H, W], 'counts': ascii str}."""
+        from . import rle
+        m = torch.as_tensor(np.asarray(binary_mask.cpu() if torch.is_tensor(binary_mask) else binary_mask)).to(torch.uint8)
+        packed = ops.mask_pack(m.cuda()[None].contiguous())
+        return rle.encode_packed(packed, m.shape[1])[0]
+
+    def score_image(self, image, raw_proposals, image_id=0, with_masks: bool = True, rle: bool = False) -> List[dict]:
+        """Annotations of one image with the reference's keys (object_scoring.py:257-267).
+        'segmentation' is {'size': [H, W], 'mask': uint8 [H, W]} (dense, for tests) or, with
+        ``rle=True``, the reference's COCO RLE dict {'size': [H, W], 'counts': str}."""
         fields = self._fields(image)
         H, W = fields.shape[-2], fields.shape[-1]
         if len(raw_proposals) == 0:
@@ -76,14 +86,17 @@ class Object_Scoring:
         keep = r["keep"][0, :n].long()
         out = r["out"][0, :n].cpu().numpy()
         bbox = r["bbox"][0, :n].cpu().numpy()
-        dense = unpack_masks(r["masks"][0][keep], W) if with_masks else None
+        dense = unpack_masks(r["masks"][0][keep], W) if (with_masks and not rle) else None
+        if with_masks and rle:
+            from . import rle as rle_codec
+            encoded = rle_codec.encode_packed(r["masks"][0][keep].contiguous(), W)
         anns = []
         for i in range(n):
             ann = {"image_id": image_id, "category_id": 1, "score": out[i, 0], "bbox": [v for v in bbox[i]],
                    "existence_score": np.float32(out[i, 1]), "center_score": np.float32(out[i, 2]),
                    "boundary_score": np.float32(out[i, 3]), "area_score": out[i, 4]}
             if with_masks:
-                ann["segmentation"] = {"size": [H, W], "mask": dense[i]}
+                ann["segmentation"] = encoded[i] if rle else {"size": [H, W], "mask": dense[i]}
             anns.append(ann)
         return anns
 

@@ -66,7 +66,7 @@ _KERNELS = {"unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_
             "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
             "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_connected_components": 1, "unmore_box_nms_matrix": 3,
             "unmore_score_and_rasterise": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
-            "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3}
+            "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3, "unmore_mask_rle_counts": 1}
 
 
 def set_timer(t: Optional[StageTimer]):
@@ -375,3 +375,16 @@ def mask_nms(packed: torch.Tensor, W: int, scores: torch.Tensor, iou_threshold: 
     _call("unmore_mask_nms", packed.data_ptr(), K, H, W, scores.data_ptr(), areas.data_ptr(), tight.data_ptr(),
               float(iou_threshold), order.data_ptr(), matrix.data_ptr(), keep.data_ptr(), kc.data_ptr(), _stream())
     return keep[: int(kc.item())].to(torch.int64)
+
+
+def mask_rle_counts(packed: torch.Tensor, W: int, max_runs: int = 4096):
+    """Packed masks [K, H, ceil(W/32)] -> (counts [K, max_runs] int32 (as uint32), n_runs [K] int32):
+    COCO column-major run lengths; rows with n_runs > max_runs are not filled."""
+    packed = packed.contiguous()
+    K, H, _ = packed.shape
+    counts = torch.zeros((K, max_runs), dtype=torch.int32, device=packed.device)
+    n_runs = torch.zeros((K,), dtype=torch.int32, device=packed.device)
+    if K:
+        _call("unmore_mask_rle_counts", packed.data_ptr(), K, H, W, int(max_runs), counts.data_ptr(), n_runs.data_ptr(),
+              _stream())
+    return counts, n_runs
