@@ -265,6 +265,29 @@ def test_rasterise_both_resize_paths_vs_oracle(dev):
     assert_rel(r["out"][0, :n, 0].cpu().numpy(), s_ref["score"], "score")
 
 
+def test_config4_shape_1024_vs_oracle(dev):
+    """configs[4] geometry: 1024x1024 fields (4093 anchors exist at that size; 96 of them + 32 random
+    boxes here so the CPU oracle finishes in seconds)."""
+    from unmore_b200.object_reasoning import Object_Discovery
+    from unmore_b200.object_scoring import Object_Scoring
+    H = W = 1024
+    img = synth.make_fields(41, H, W)
+    anchors = synth.anchor_proposals(H, W)
+    assert anchors.shape == (4093, 4)
+    props = np.concatenate([anchors[::43], synth.random_proposals(41, 32, H, W), anchors[-1:]])
+    args = O.make_args()
+    ref = O.discover_image(img, props, args)
+    odl = Object_Discovery(device=dev)
+    det = odl.discover_image(img.to(dev), props)
+    assert_boxes_close(det, ref, "1024x1024 discovery")
+    if len(ref):
+        s_ref = O.score_image(img, ref.tolist(), args)
+        anns = Object_Scoring(device=dev).score_image(img.to(dev), ref.astype(np.float64).tolist())
+        assert np.array_equal(np.array([a["bbox"] for a in anns], np.float32), s_ref["bbox"])
+        assert np.array_equal(np.stack([a["segmentation"]["mask"] for a in anns]), s_ref["masks"])
+        assert_rel([a["score"] for a in anns], s_ref["score"], "score")
+
+
 def test_batch_equals_single_and_ragged(dev, od):
     """Images are independent: a ragged batch must reproduce the per-image results exactly."""
     ids = [3, 4, 5, 6]

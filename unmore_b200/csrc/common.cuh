@@ -35,17 +35,16 @@ struct AxisTap {
 };
 
 __device__ __forceinline__ AxisTap axis_tap(float scale, int i, int in_size) {
-  float src = __fmaf_rn(scale, (float)i + 0.5f, -0.5f);
-  src = src < 0.f ? 0.f : src;
-  int i0 = (int)src;
-  i0 = i0 < in_size - 1 ? i0 : in_size - 1;
+  // ATen clamps lambda to [0, 1]; that clamp can never bind here: src >= 0 after the max, i0 is
+  // either floor(src) (lambda in [0,1)) or the clamped last index, and src < in - 0.5 keeps
+  // src - (in-1) < 0.5.  Dropping it removes three instructions from every output row.
+  const float src = fmaxf(__fmaf_rn(scale, (float)i + 0.5f, -0.5f), 0.f);
+  const int i0 = min((int)src, in_size - 1);
   AxisTap t;
   t.i0 = i0;
-  t.i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
-  float l1 = __fsub_rn(src, (float)i0);
-  l1 = l1 < 0.f ? 0.f : (l1 > 1.f ? 1.f : l1);
-  t.l1 = l1;
-  t.l0 = __fsub_rn(1.f, l1);
+  t.i1 = min(i0 + 1, in_size - 1);
+  t.l1 = __fsub_rn(src, (float)i0);
+  t.l0 = __fsub_rn(1.f, t.l1);
   return t;
 }
 

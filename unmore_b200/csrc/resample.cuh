@@ -19,6 +19,14 @@ namespace unmore {
 
 enum ColLayout { kBlocked = 0, kStrided = 1 };
 
+// base + idx (elements) as ONE IMAD.WIDE on a 64-bit base held in registers; without this the
+// compiler re-derives the window origin per tap (IADD3 + LEA.HI.X.SX32 + LEA + LEA.HI.X).
+__device__ __forceinline__ const float* elem_ptr(const float* base, int idx) {
+  const float* r;
+  asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(base));
+  return r;
+}
+
 template <int LAYOUT>
 __device__ __forceinline__ int lane_column(int lane, int c) {
   return LAYOUT == kStrided ? lane + 32 * c : 4 * lane + c;
@@ -58,7 +66,7 @@ struct PlaneRows {
     const int ro = y * stride;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float* q = origin + (ro + t.x0[c]);
+      const float* q = elem_ptr(origin, ro + t.x0[c]);
       const float v0 = __ldg(q);
       float v1 = v0;
       if (t.two[c]) v1 = __ldg(q + 1);
@@ -80,7 +88,7 @@ struct PlaneRows {
     const int ro = y * stride;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float* q = origin + (ro + t.x0[c]);
+      const float* q = elem_ptr(origin, ro + t.x0[c]);
       v0[c] = __ldg(q);
       v1[c] = v0[c];
       if (t.two[c]) v1[c] = __ldg(q + 1);

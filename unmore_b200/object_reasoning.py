@@ -247,7 +247,12 @@ class Object_Discovery:
                                               max_sdf_thres=a.max_sdf_thres,
                                               max_shrink_threshold=a.max_shrink_threshold, delta_ratio=a.delta_ratio,
                                               ch=ch, ws=ws, want_rounds=stats is not None)
-        fin, fc, _ = ops.compact_boxes(rb, rc, ops.MODE_LABEL_EQ, lab, thr=1.0, out_dtype=torch.float32)
+        # label-1 survivors; the NMS kernel holds its alive set for at most 32768 boxes per image
+        lost1 = torch.zeros((1,), dtype=torch.int32, device=dev) if cap_out > 32768 else None
+        fin, fc, _ = ops.compact_boxes(rb, rc, ops.MODE_LABEL_EQ, lab, thr=1.0, out_dtype=torch.float32,
+                                       cap_out=min(cap_out, 32768), overflow=lost1)
+        if lost1 is not None and int(lost1.item()):
+            raise RuntimeError("more than 32768 label-1 boxes in one image")
         # NMS with all-equal scores (:661): index order decides
         _, kc, kb = ops.box_nms(fin, None, fc, iou_threshold=0.5)
         if stats is not None:
