@@ -227,11 +227,16 @@ def main():
     launches0 = ops.LAUNCHES
     ops.set_timer(timer)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = os.environ.get("UNMORE_PROFILE_RANGE") == "1"   # ncu --profile-from-start off: timed region only
+    if prof_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         out = step()
     ev1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     ops.set_timer(None)
     clocks = sampler.stop()
     launches = ops.LAUNCHES - launches0

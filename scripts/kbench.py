@@ -15,7 +15,8 @@ anch = synth.anchor_proposals(H, W)
 props = torch.from_numpy(np.stack([np.concatenate([anch, synth.random_proposals(i, N - len(anch), H, W)]) for i in range(n_img)])).to(dev)
 od = Object_Discovery(device=dev)
 st = {}
-kb, kc = od.discover_batch(fields, props, stats=st)
+if which & {"all", "center", "refine", "score"}:
+    kb, kc = od.discover_batch(fields, props, stats=st)
 torch.cuda.synchronize()
 
 def timeit(fn, reps=5):
@@ -52,8 +53,14 @@ if which & {"all", "score"}:
     det = kb[:, :cap].contiguous()
     mn, av = timeit(lambda: ops.score_and_rasterise(fields, det, kc))
     print(f"score   : {mn:8.3f} ms min {av:8.3f} avg  ({int(kc.sum())} boxes)")
+if which & {"pack"}:
+    K = 2048
+    dense = (torch.rand((K, H, W), device=dev) < 0.3).to(torch.uint8)
+    mn, av = timeit(lambda: ops.mask_pack(dense))
+    b = K * H * W + K * H * ((W + 31) // 32) * 4
+    print(f"pack    : {mn:8.3f} ms min {av:8.3f} avg  {b/mn/1e6:8.1f} GB/s ({b/1e6:.0f} MB)")
 if which & {"all", "sat"}:
-    planes = torch.stack([fields[:, 3], fields[:, 0]], dim=1).contiguous()
-    mn, av = timeit(lambda: ops.sat_build(planes))
-    b = planes.numel() * 4 + planes.shape[0] * 2 * (H + 1) * (W + 1) * 8
+    out_buf = torch.empty((n_img, 2, H + 1, W + 1), dtype=torch.float64, device=dev)
+    mn, av = timeit(lambda: ops.sat_build_fields(fields, [3, 0], out=out_buf))
+    b = n_img * 2 * (H * W * 4 + (H + 1) * (W + 1) * 8)
     print(f"sat     : {mn:8.3f} ms min {av:8.3f} avg  {b/mn/1e6:8.1f} GB/s ({b/1e6:.0f} MB)")

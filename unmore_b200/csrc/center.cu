@@ -159,9 +159,22 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const int i = warp * (kCrop / kCenterWarps) + ii;
         const AxisTap v = axis_tap(scale_y, i, in_h);
         float s[4], a[4], b[4];
+#ifdef UNMORE_CENTER_SPLIT_LOADS
+        {  // all three channels' taps in flight before any is consumed
+          const int mode = ps.plan(v);
+          PlaneRows::Raw r0, r1, r2;
+          ps.issue(taps, v, mode, r0);
+          p0.issue(taps, v, mode, r1);
+          p1.issue(taps, v, mode, r2);
+          ps.finish(taps, v, mode, r0, s);
+          p0.finish(taps, v, mode, r1, a);
+          p1.finish(taps, v, mode, r2, b);
+        }
+#else
         ps.row(taps, v, s);
         p0.row(taps, v, a);
         p1.row(taps, v, b);
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int j = lane + 32 * c;

@@ -17,17 +17,26 @@ __device__ __forceinline__ uint32_t nz4(uint32_t w) {  // 4 bytes -> 4 bits (byt
   return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
 }
 
-// fast path: W % 32 == 0.  Lane loads 16 pixels (one uint4), pairs of lanes form a word.
+// fast path: W % 32 == 0.  A lane loads 16 pixels (one uint4), pairs of lanes form a word; each
+// thread keeps four independent 16-byte loads in flight (grid-stride unrolled) to cover HBM latency.
+constexpr int kPackUnroll = 4;
 __global__ void __launch_bounds__(256) pack_kernel_vec(const uint4* __restrict__ in, uint32_t* __restrict__ out,
                                                        size_t n_vec) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t bits = 0;
-  if (i < n_vec) {
-    const uint4 v = __ldcs(in + i);
-    bits = nz4(v.x) | (nz4(v.y) << 4) | (nz4(v.z) << 8) | (nz4(v.w) << 12);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 v[kPackUnroll];
+#pragma unroll
+  for (int u = 0; u < kPackUnroll; ++u) {
+    const size_t i = i0 + u * stride;
+    v[u] = i < n_vec ? __ldcs(in + i) : make_uint4(0u, 0u, 0u, 0u);
   }
-  const uint32_t hi = __shfl_down_sync(kFullMask, bits, 1);
-  if (!(threadIdx.x & 1) && i < n_vec) __stcs(out + (i >> 1), bits | (hi << 16));
+#pragma unroll
+  for (int u = 0; u < kPackUnroll; ++u) {
+    const size_t i = i0 + u * stride;
+    const uint32_t bits = nz4(v[u].x) | (nz4(v[u].y) << 4) | (nz4(v[u].z) << 8) | (nz4(v[u].w) << 12);
+    const uint32_t hi = __shfl_down_sync(kFullMask, bits, 1);
+    if (!(threadIdx.x & 1) && i < n_vec) __stcs(out + (i >> 1), bits | (hi << 16));
+  }
 }
 
 __global__ void __launch_bounds__(256) pack_kernel_generic(const unsigned char* __restrict__ in,
@@ -48,7 +57,8 @@ int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int
   const int Wp = (W + 31) >> 5;
   if ((W & 31) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
     const size_t n_vec = n_masks * H * (size_t)W / 16;
-    pack_kernel_vec<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), out, n_vec);
+    const size_t per_block = 256 * (size_t)kPackUnroll;   // n_vec is even (W % 32 == 0), so lane pairs never straddle strides
+    pack_kernel_vec<<<(unsigned)((n_vec + per_block - 1) / per_block), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), out, n_vec);
   } else {
     const size_t total = n_masks * H * (size_t)Wp;
     pack_kernel_generic<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, n_masks * (size_t)H, W, Wp);
