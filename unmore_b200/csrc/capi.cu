@@ -1,6 +1,6 @@
 // C-ABI entry points (include/unmore_b200.h).  Argument checking, workspace carving and
 // kernel launches only; no device allocation, no synchronisation, no global mutable state
-// other than cached device attributes and the thread-local error string.
+// other than the thread-local error string.
 #include <cstdio>
 #include <cstdarg>
 #include <cmath>
@@ -29,17 +29,12 @@ int cuda_fail(int code, const char* what) {
   return code;
 }
 
-int num_sms() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
-  }
-  return cached;
+int num_sms() {  // of the current device; a plain attribute query, no cached state
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    return n;
+  return 148;
 }
 
 // ws layout: [0] work counter, [1 .. n_img+1] exclusive prefix of counts

@@ -159,22 +159,9 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const int i = warp * (kCrop / kCenterWarps) + ii;
         const AxisTap v = axis_tap(scale_y, i, in_h);
         float s[4], a[4], b[4];
-#ifdef UNMORE_CENTER_SPLIT_LOADS
-        {  // all three channels' taps in flight before any is consumed
-          const int mode = ps.plan(v);
-          PlaneRows::Raw r0, r1, r2;
-          ps.issue(taps, v, mode, r0);
-          p0.issue(taps, v, mode, r1);
-          p1.issue(taps, v, mode, r2);
-          ps.finish(taps, v, mode, r0, s);
-          p0.finish(taps, v, mode, r1, a);
-          p1.finish(taps, v, mode, r2, b);
-        }
-#else
         ps.row(taps, v, s);
         p0.row(taps, v, a);
         p1.row(taps, v, b);
-#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int j = lane + 32 * c;
@@ -501,25 +488,19 @@ __global__ void __launch_bounds__(kCenterThreads) components_kernel(const unsign
 
 int launch_components(const unsigned char* masks, int B, int* counts, int* boxes, cudaStream_t stream) {
   if (B <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcSmem));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  // function attributes are per device: set on every launch (microseconds), no cached state
+  cudaError_t e = cudaFuncSetAttribute(components_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcSmem));
+  if (e != cudaSuccess) return (int)e;
   components_kernel<<<B, kCenterThreads, sizeof(CcSmem), stream>>>(masks, B, counts, boxes);
   return (int)cudaGetLastError();
 }
 
 int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(center_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(center_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  // function attributes are per device: set on every launch (microseconds), no cached state
+  cudaError_t e = p.cc_counts
+      ? cudaFuncSetAttribute(center_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem))
+      : cudaFuncSetAttribute(center_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+  if (e != cudaSuccess) return (int)e;
   if (p.cc_counts) center_kernel<true><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
   else center_kernel<false><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
   return (int)cudaGetLastError();

@@ -35,16 +35,9 @@ __device__ __forceinline__ float soft_fg(float s) {
 
 struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
   const float* tile;
-  struct Pending { float4 v; };
   __device__ __forceinline__ void row(int lane, int i, float out[4]) const {
     const float4 v = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
     out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-  }
-  __device__ __forceinline__ void issue(int lane, int i, Pending& p) const {
-    p.v = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
-  }
-  __device__ __forceinline__ void finish(const Pending& p, float out[4]) const {
-    out[0] = p.v.x; out[1] = p.v.y; out[2] = p.v.z; out[3] = p.v.w;
   }
 };
 
@@ -53,31 +46,8 @@ struct CropRows {  // crop window of the boundary-distance channel, resampled on
   PlaneRows plane;
   float scale_y;
   int in_h;
-  int pf_off;   // this lane's 128-byte line of a source row (element offset), or -1
-  __device__ __forceinline__ void init_prefetch(int lane, int in_w) {
-    pf_off = (32 * lane < in_w + 32) ? 32 * lane : -1;
-  }
-  struct Pending { AxisTap v; int mode; PlaneRows::Raw raw; };
-  __device__ __forceinline__ void issue(int /*lane*/, int i, Pending& p) const {
-    p.v = axis_tap(scale_y, i, in_h);
-    p.mode = plane.plan(p.v);
-    plane.issue(taps, p.v, p.mode, p.raw);
-  }
-  __device__ __forceinline__ void finish(const Pending& p, float out[4]) { plane.finish(taps, p.v, p.mode, p.raw, out); }
   __device__ __forceinline__ void row(int /*lane*/, int i, float out[4]) {
     plane.row(taps, axis_tap(scale_y, i, in_h), out);
-#ifdef UNMORE_L1_PREFETCH
-    // Pull the source rows of the NEXT output row into L1 now (one 128-byte line per lane), so
-    // its taps hit L1 (~40 cycles) instead of waiting a full L2 round trip (~300 cycles).
-    if (pf_off >= 0) {
-      float src = __fmaf_rn(scale_y, (float)i + 1.5f, -0.5f);
-      int yn = (int)fmaxf(src, 0.f);
-      yn = min(yn, in_h - 1);
-      const float* q = plane.origin + (yn * plane.stride + pf_off);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
-      if (yn + 1 < in_h) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + plane.stride));
-    }
-#endif
   }
 };
 
@@ -107,7 +77,6 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     const float right = __shfl_down_sync(kFullMask, cur[0], 1);  // S[i][4l+4]
     if (lane == 0) cols.left[i] = cur[0];     // column 0
     if (lane == 31) cols.right[i] = cur[2];   // column 126
-#ifndef UNMORE_NO_ILP
     // the four pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a);
     // stage them so the MUFU latencies overlap instead of serialising pixel after pixel
     float t[4], u[4], g[4], a[4];
@@ -136,24 +105,6 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
       }
       mx = fmaxf(mx, nxt[c]);
     }
-#else
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float s = cur[c];
-      const float dxv = (c < 3 ? cur[c + 1] : right) - s;
-      const float dyv = nxt[c] - s;
-      const float g = sqrt_approx(fmaf(dyv, dyv, dxv * dxv));  // ||grad||; only feeds the averaged sums
-      const float a = soft_fg(s);
-      const float b = 1.f - a;
-      if ((c < 3) || (lane < 31)) {  // column 127 is outside the 127x127 region
-        fA += a;
-        fAg = fmaf(a, g, fAg);
-        fB += b;
-        fBg = fmaf(b, g, fBg);
-      }
-      mx = fmaxf(mx, nxt[c]);
-    }
-#endif
   };
   // fp32 partial sums are flushed into fp64 every 8 rows (32 px per lane): keeps the
   // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
@@ -162,27 +113,6 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     fA = fAg = fB = fBg = 0.f;
   };
   // rows ping-pong between ra / rb so no register copies are needed
-#ifdef UNMORE_REFINE_PIPELINE
-  // software pipeline: the taps of output row i+2 are requested before row i is reduced and
-  // consumed after it, so their L1/L2 latency hides behind ~100 instructions of math
-  typename RowSrc::Pending pend;
-  src.row(lane, 1, rb);
-  src.issue(lane, 2, pend);
-  for (int i = 0; i < kCrop - 2; i += 2) {
-    process(ra, rb, i);
-    src.finish(pend, ra);                       // row i+2
-    src.issue(lane, min(i + 3, kCrop - 1), pend);
-    process(rb, ra, i + 1);
-    src.finish(pend, rb);                       // row i+3
-    if (i + 4 < kCrop) src.issue(lane, i + 4, pend);
-    if ((i & 7) == 6) flush();
-  }
-  // i = 126: ra holds row 126, rb row 127
-#pragma unroll
-  for (int c = 0; c < 4; ++c) bot[c] = ra[c];
-  process(ra, rb, kCrop - 2);
-  flush();
-#else
   for (int i = 0; i < kCrop - 2; i += 2) {
     src.row(lane, i + 1, rb);
     process(ra, rb, i);
@@ -196,7 +126,6 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
   src.row(lane, kCrop - 1, rb);
   process(ra, rb, kCrop - 2);
   flush();
-#endif
   Deltas d;
   d.max_sdf = warp_max(mx);
   const float sumA = (float)warp_sum(dA);
@@ -252,7 +181,6 @@ __device__ __forceinline__ int one_round(const RefineParams& p, const float* pla
   src.plane.init(plane, p.W, win);
   src.in_h = win.h();
   src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
-  src.init_prefetch(lane, win.w());
   const Deltas d = boundary_terms(src, cols, lane);
   if (!(d.max_sdf > p.max_sdf_thres)) return -1;
   // signed deltas: >0 expands, <0 shrinks; expansion is ignored on sides glued to the image edge (:444-447)

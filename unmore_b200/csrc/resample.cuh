@@ -34,8 +34,7 @@ __device__ __forceinline__ int lane_column(int lane, int c) {
 
 // Column taps of this lane for the current window, shared by all channels.
 struct ColTaps {
-  int x0[4];
-  bool two[4];  // second tap is x0+1 (false only on the clamped right edge, where it repeats x0)
+  int x0[4], x1[4];   // x1 = x0 + 1, or x0 again on the clamped right edge
   float w0[4], w1[4];
   template <int LAYOUT>
   __device__ __forceinline__ void init(int lane, int in_w) {
@@ -43,7 +42,7 @@ struct ColTaps {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       AxisTap t = axis_tap(scale, lane_column<LAYOUT>(lane, c), in_w);
-      x0[c] = t.i0; two[c] = t.i1 != t.i0; w0[c] = t.l0; w1[c] = t.l1;
+      x0[c] = t.i0; x1[c] = t.i1; w0[c] = t.l0; w1[c] = t.l1;
     }
   }
 };
@@ -61,65 +60,19 @@ struct PlaneRows {
     cy0 = cy1 = -1;
   }
   __device__ __forceinline__ void hrow(const ColTaps& t, int y, float out[4]) const {
-    // 32-bit element offsets from the window origin: one IADD + one IMAD.WIDE per column, the
-    // second tap rides on the same address (+4 bytes, predicated off on the clamped edge)
+    // 32-bit element offsets from the window origin, one address per tap.  Both taps of all four
+    // columns are independent loads (no "v1 = v0 unless ..." dependency), so the eight requests of
+    // a source row go out back to back and cost one memory round trip.
     const int ro = y * stride;
+    float v0[4], v1[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float* q = elem_ptr(origin, ro + t.x0[c]);
-      const float v0 = __ldg(q);
-      float v1 = v0;
-      if (t.two[c]) v1 = __ldg(q + 1);
-      out[c] = lerp_h(v0, v1, t.w0[c], t.w1[c]);
-    }
-  }
-  // ---- split-phase variant: plan() decides which source rows are new, issue() only starts their
-  // loads (raw taps into registers), finish() consumes them.  Work placed between issue() and
-  // finish() overlaps the L1/L2 latency of the loads.
-  //   mode bit0: fetch row i0 -> a;  bit1: fetch row i1 -> b;  bit2: ra <- rb;  bit3: rb <- ra
-  struct Raw { float a0[4], a1[4], b0[4], b1[4]; };
-  __device__ __forceinline__ int plan(const AxisTap& v) const {
-    if (v.i0 == cy0 && v.i1 == cy1) return 0;
-    int m = (v.i0 == cy1) ? 4 : 1;
-    m |= (v.i1 != v.i0) ? 2 : 8;
-    return m;
-  }
-  __device__ __forceinline__ void load_raw(const ColTaps& t, int y, float v0[4], float v1[4]) const {
-    const int ro = y * stride;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float* q = elem_ptr(origin, ro + t.x0[c]);
-      v0[c] = __ldg(q);
-      v1[c] = v0[c];
-      if (t.two[c]) v1[c] = __ldg(q + 1);
-    }
-  }
-  __device__ __forceinline__ void issue(const ColTaps& t, const AxisTap& v, int mode, Raw& r) const {
-    if (mode & 1) load_raw(t, v.i0, r.a0, r.a1);
-    if (mode & 2) load_raw(t, v.i1, r.b0, r.b1);
-  }
-  __device__ __forceinline__ void finish(const ColTaps& t, const AxisTap& v, int mode, const Raw& r, float out[4]) {
-    if (mode) {
-      if (mode & 4) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ra[c] = rb[c];
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ra[c] = lerp_h(r.a0[c], r.a1[c], t.w0[c], t.w1[c]);
-      }
-      if (mode & 2) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rb[c] = lerp_h(r.b0[c], r.b1[c], t.w0[c], t.w1[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rb[c] = ra[c];
-      }
-      cy0 = v.i0; cy1 = v.i1;
+      v0[c] = __ldg(elem_ptr(origin, ro + t.x0[c]));
+      v1[c] = __ldg(elem_ptr(origin, ro + t.x1[c]));
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = lerp_v(ra[c], rb[c], v.l0, v.l1);
+    for (int c = 0; c < 4; ++c) out[c] = lerp_h(v0[c], v1[c], t.w0[c], t.w1[c]);
   }
-
   // S[i][lane_column(lane, c)], c = 0..3, for the output row whose vertical tap is `v`
   __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[4]) {
     if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform

@@ -179,12 +179,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
 
 int launch_score(const ScoreParams& p, cudaStream_t stream) {
   if (p.n_img <= 0 || p.cap <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem));
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem));
+  if (e != cudaSuccess) return (int)e;
   dim3 grid(p.cap, p.n_img);
   score_kernel<<<grid, kScoreThreads, sizeof(ScoreSmem), stream>>>(p);
   return (int)cudaGetLastError();
