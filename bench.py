@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--images", type=int, default=5000, help="images per rank and step")
     ap.add_argument("--proposals", type=int, default=N_PROP)
     ap.add_argument("--chunk", type=int, default=250, help="images per launch group")
-    ap.add_argument("--cpu-sample-proposals", type=int, default=256)
+    ap.add_argument("--cpu-sample-proposals", type=int, default=1536,
+                    help="proposals of image 0 the CPU baseline / reference arm processes per sample (~7 s on 16 cores)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -283,7 +284,7 @@ def main():
         need = n_img * 4 * px * 4
         pool = n_img
         avail = psutil.virtual_memory().available
-        while pool > chunk and pool * 4 * px * 4 > avail // 4:
+        while pool > chunk and pool * 4 * px * 4 * world > avail // 4:   # every rank pins its own pool
             pool //= 2
         pool = max(chunk, (pool // chunk) * chunk)
         h_fields = torch.empty((pool, 4, H, W), dtype=torch.float32).pin_memory()

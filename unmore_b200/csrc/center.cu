@@ -148,20 +148,21 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       taps.init<kStrided>(lane, win.w());
       const size_t plane_sz = (size_t)p.H * p.W;
       const float* base = p.fields + (size_t)img * p.C * plane_sz;
-      PlaneRows ps, p0, p1;
-      ps.init(base + p.ch_sdf * plane_sz, p.W, win);
-      p0.init(base + p.ch_crow * plane_sz, p.W, win);
-      p1.init(base + p.ch_ccol * plane_sz, p.W, win);
+      const float* const planes[3] = {base + p.ch_sdf * plane_sz, base + p.ch_crow * plane_sz,
+                                      base + p.ch_ccol * plane_sz};
+      MultiPlaneRows<3> rows;
+      rows.init(planes, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
       float cabs = 0.f;  // max |center field| over the staged window: scales the fp32 screening margin
       for (int ii = 0; ii < kCrop / kCenterWarps; ++ii) {
         const int i = warp * (kCrop / kCenterWarps) + ii;
         const AxisTap v = axis_tap(scale_y, i, in_h);
-        float s[4], a[4], b[4];
-        ps.row(taps, v, s);
-        p0.row(taps, v, a);
-        p1.row(taps, v, b);
+        float sab[3][4];
+        rows.row(taps, v, sab);
+        const float (&s)[4] = sab[0];
+        const float (&a)[4] = sab[1];
+        const float (&b)[4] = sab[2];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int j = lane + 32 * c;

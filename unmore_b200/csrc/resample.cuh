@@ -95,4 +95,64 @@ struct PlaneRows {
   }
 };
 
+// P channel planes of one window behind ONE row cache: the (cy0, cy1) bookkeeping and its branches
+// run once per output row instead of once per plane, and the taps of all planes of a source row
+// are requested together before any is consumed (P x 8 loads in flight).
+template <int P>
+struct MultiPlaneRows {
+  const float* origin[P];
+  int stride;
+  int cy0, cy1;
+  float ra[P][4], rb[P][4];
+
+  __device__ __forceinline__ void init(const float* const planes[P], int W, const Window& win) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) origin[p] = planes[p] + (size_t)win.y1 * W + win.x1;
+    stride = W;
+    cy0 = cy1 = -1;
+  }
+  __device__ __forceinline__ void hrows(const ColTaps& t, int y, float out[P][4]) const {
+    const int ro = y * stride;
+    float v0[P][4], v1[P][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i0 = ro + t.x0[c], i1 = ro + t.x1[c];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        v0[p][c] = __ldg(elem_ptr(origin[p], i0));
+        v1[p][c] = __ldg(elem_ptr(origin[p], i1));
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out[p][c] = lerp_h(v0[p][c], v1[p][c], t.w0[c], t.w1[c]);
+  }
+  __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[P][4]) {
+    if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
+      if (v.i0 == cy1) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ra[p][c] = rb[p][c];
+      } else {
+        hrows(t, v.i0, ra);
+      }
+      if (v.i1 == v.i0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) rb[p][c] = ra[p][c];
+      } else {
+        hrows(t, v.i1, rb);
+      }
+      cy0 = v.i0; cy1 = v.i1;
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out[p][c] = lerp_v(ra[p][c], rb[p][c], v.l0, v.l1);
+  }
+};
+
 }  // namespace unmore

@@ -62,11 +62,10 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
     taps.init<kStrided>(lane, win.w());
     const size_t plane_sz = (size_t)p.H * p.W;
     const float* base = p.fields + (size_t)img * p.C * plane_sz;
-    PlaneRows ps, p0, p1, pe;
-    ps.init(base + p.ch_sdf * plane_sz, p.W, win);
-    p0.init(base + p.ch_crow * plane_sz, p.W, win);
-    p1.init(base + p.ch_ccol * plane_sz, p.W, win);
-    pe.init(base + p.ch_exist * plane_sz, p.W, win);
+    const float* const planes[4] = {base + p.ch_sdf * plane_sz, base + p.ch_crow * plane_sz,
+                                    base + p.ch_ccol * plane_sz, base + p.ch_exist * plane_sz};
+    MultiPlaneRows<4> rows;
+    rows.init(planes, p.W, win);
     const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
     const int in_h = win.h();
     double esum = 0.0;
@@ -75,11 +74,12 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
     for (int ii = 0; ii < kRows; ++ii) {
       const int i = warp * kRows + ii;
       const AxisTap v = axis_tap(scale_y, i, in_h);
-      float s[4], a[4], b[4], e[4];
-      ps.row(taps, v, s);
-      p0.row(taps, v, a);
-      p1.row(taps, v, b);
-      pe.row(taps, v, e);
+      float sabe[4][4];
+      rows.row(taps, v, sabe);
+      const float (&s)[4] = sabe[0];
+      const float (&a)[4] = sabe[1];
+      const float (&b)[4] = sabe[2];
+      const float (&e)[4] = sabe[3];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float sq = __fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c]));  // torch.norm order
