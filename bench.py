@@ -347,22 +347,12 @@ def main():
         e2e = {"value": world * n_img / dt, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "host_pool_images": pool, "ms_per_step": dt * 1e3}
 
-    # ---- configs[2] side measurement (outside the step): HBM-streaming mask bit-pack and mask-IoU NMS
+    # ---- configs[2] side measurement (outside the step): mask bit-pack (HBM streaming) and the
+    # mask-IoU / box NMS sweep at 1k - 16k masks per image, 480x640
     extras = {}
     if rank == 0 and not args.no_extras:
         del sat_buf
         torch.cuda.empty_cache()
-        K = 4096
-        g = torch.Generator(device=dev).manual_seed(0)
-        dense = torch.zeros((K, H, W), dtype=torch.uint8, device=dev)
-        cx = torch.rand(K, generator=g, device=dev) * W; cy = torch.rand(K, generator=g, device=dev) * H
-        rx = 20 + torch.rand(K, generator=g, device=dev) * 120; ry = 20 + torch.rand(K, generator=g, device=dev) * 120
-        ys = torch.arange(H, device=dev).view(1, H, 1); xs = torch.arange(W, device=dev).view(1, 1, W)
-        for k0 in range(0, K, 256):
-            sl = slice(k0, k0 + 256)
-            dense[sl] = ((((ys - cy[sl].view(-1, 1, 1)) / ry[sl].view(-1, 1, 1)) ** 2 +
-                          ((xs - cx[sl].view(-1, 1, 1)) / rx[sl].view(-1, 1, 1)) ** 2) < 1).to(torch.uint8)
-        msc = torch.rand(K, generator=g, device=dev)
 
         def timed(fn, reps=5):
             fn(); torch.cuda.synchronize()
@@ -372,15 +362,34 @@ def main():
                 a.record(); fn(); b.record(); torch.cuda.synchronize()
                 best = min(best, a.elapsed_time(b))
             return best
-        t_pack = timed(lambda: ops.mask_pack(dense))
-        packed = ops.mask_pack(dense)
-        pack_bytes = K * H * W + K * H * ((W + 31) // 32) * 4
-        t_nms = timed(lambda: ops.mask_nms(packed, W, msc, 0.5), reps=3)
-        kept = int(ops.mask_nms(packed, W, msc, 0.5).numel())
-        extras = {"mask_pack": {"masks": K, "ms": t_pack, "achieved_gbs": pack_bytes / t_pack / 1e6,
-                                "frac": pack_bytes / t_pack / 1e6 / hbm_peak, "bound": "hbm"},
-                  "mask_nms": {"masks": K, "ms": t_nms, "kept": kept, "note": "stats + rank sort + bit-matrix + greedy scan"}}
-        del dense, packed
+
+        g = torch.Generator(device=dev).manual_seed(0)
+        ys = torch.arange(H, device=dev).view(1, H, 1); xs = torch.arange(W, device=dev).view(1, 1, W)
+        sweep = []
+        for K in (1024, 4096, 16384):
+            dense = torch.empty((K, H, W), dtype=torch.uint8, device=dev)
+            cx = torch.rand(K, generator=g, device=dev) * W; cy = torch.rand(K, generator=g, device=dev) * H
+            rx = 20 + torch.rand(K, generator=g, device=dev) * 120; ry = 20 + torch.rand(K, generator=g, device=dev) * 120
+            for k0 in range(0, K, 256):
+                sl = slice(k0, k0 + 256)
+                dense[sl] = ((((ys - cy[sl].view(-1, 1, 1)) / ry[sl].view(-1, 1, 1)) ** 2 +
+                              ((xs - cx[sl].view(-1, 1, 1)) / rx[sl].view(-1, 1, 1)) ** 2) < 1).to(torch.uint8)
+            msc = torch.rand(K, generator=g, device=dev)
+            t_pack = timed(lambda: ops.mask_pack(dense))
+            packed = ops.mask_pack(dense)
+            del dense
+            pack_bytes = K * H * W + K * H * ((W + 31) // 32) * 4
+            stats_ = ops.mask_stats(packed, W)
+            t_nms = timed(lambda: ops.mask_nms(packed, W, msc, 0.5, stats=stats_), reps=3)
+            kept = int(ops.mask_nms(packed, W, msc, 0.5, stats=stats_).numel())
+            boxes = stats_[1].to(torch.float32)
+            t_box = timed(lambda: ops.box_nms_matrix(boxes, msc, 0.5), reps=3)
+            sweep.append({"masks": K, "pack_ms": t_pack, "pack_gbs": pack_bytes / t_pack / 1e6,
+                          "pack_frac_of_hbm_peak": pack_bytes / t_pack / 1e6 / hbm_peak,
+                          "mask_nms_ms": t_nms, "mask_nms_kept": kept, "box_nms_matrix_ms": t_box})
+            del packed
+        extras = {"nms_sweep_480x640": sweep,
+                  "note": "configs[2]; mask_nms = rank sort + 64-wide IoU bit-matrix (popc on packed masks) + greedy scan"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

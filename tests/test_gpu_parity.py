@@ -420,6 +420,23 @@ def test_scoring_with_rle_segmentation(golden_dir, dev):
     assert rle.scored_annotations_json(anns).startswith("[")
 
 
+@pytest.mark.parametrize("K", [1000, 16384])
+def test_box_nms_sweep_sizes(dev, ops, K):
+    """configs[2] sizes: 1k and 16k boxes per image, per-image kernel and matrix kernel, vs the oracle."""
+    rng = np.random.default_rng(K)
+    c = rng.uniform(0, 600, (K, 2)).astype(np.float32)
+    wh = rng.uniform(8, 160, (K, 2)).astype(np.float32)
+    boxes = np.concatenate([c, c + wh], axis=1)
+    scores = rng.random(K).astype(np.float32)
+    scores[::7] = 0.25                       # many exact ties
+    ref = O.nms(boxes, scores, 0.5)
+    b = torch.tensor(boxes, device=dev)
+    s = torch.tensor(scores, device=dev)
+    assert np.array_equal(ops.box_nms_matrix(b, s).cpu().numpy(), ref)
+    keep, kc, _ = ops.box_nms(b[None].contiguous(), s[None].contiguous())
+    assert np.array_equal(keep[0, : int(kc[0])].cpu().numpy(), ref)
+
+
 # ------------------------------------------------------------------------------------------
 # full-size properties (configs[1] shapes: 480x640 fields, 4096 proposals per image)
 # ------------------------------------------------------------------------------------------
