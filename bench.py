@@ -388,7 +388,27 @@ def main():
                           "pack_frac_of_hbm_peak": pack_bytes / t_pack / 1e6 / hbm_peak,
                           "mask_nms_ms": t_nms, "mask_nms_kept": kept, "box_nms_matrix_ms": t_box})
             del packed
-        extras = {"nms_sweep_480x640": sweep,
+        # CPU side of the sweep: the dense-mask greedy restatement (oracle, north-star op C) on 256 masks
+        cpu_nms = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            Kc = 256
+            dense = torch.empty((Kc, H, W), dtype=torch.uint8, device=dev)
+            cx = torch.rand(Kc, generator=g, device=dev) * W; cy = torch.rand(Kc, generator=g, device=dev) * H
+            rx = 20 + torch.rand(Kc, generator=g, device=dev) * 120; ry = 20 + torch.rand(Kc, generator=g, device=dev) * 120
+            dense[:] = ((((ys - cy.view(-1, 1, 1)) / ry.view(-1, 1, 1)) ** 2 + ((xs - cx.view(-1, 1, 1)) / rx.view(-1, 1, 1)) ** 2) < 1).to(torch.uint8)
+            msc = torch.rand(Kc, generator=g, device=dev)
+            packed = ops.mask_pack(dense)
+            t_gpu = timed(lambda: ops.mask_nms(packed, W, msc, 0.5), reps=3)
+            keep_gpu = ops.mask_nms(packed, W, msc, 0.5).cpu().numpy()
+            dn, sn = dense.cpu().numpy(), msc.cpu().numpy()
+            t0 = time.perf_counter()
+            keep_cpu = O.mask_nms_dense(dn, sn, 0.5)
+            t_cpu = (time.perf_counter() - t0) * 1e3
+            cpu_nms = {"masks": Kc, "cpu_dense_ms": t_cpu, "gpu_ms_incl_stats": t_gpu, "keep_sets_equal": bool(np.array_equal(keep_gpu, keep_cpu)),
+                       "kind": "port (numpy, 1 core)"}
+            del dense, packed
+        extras = {"cpu_mask_nms": cpu_nms, "nms_sweep_480x640": sweep,
                   "note": "configs[2]; mask_nms = rank sort + 64-wide IoU bit-matrix (popc on packed masks) + greedy scan"}
 
     cpu_baseline = None

@@ -116,49 +116,68 @@ __global__ void __launch_bounds__(256) rank_sort_kernel(const float* __restrict_
 }
 
 // ---- suppression bit-matrix --------------------------------------------------------------
-// grid (cb, rb) with cb >= rb; thread t of the CTA owns sorted row rb*64+t against the 64 sorted
-// columns of block cb.  matrix[r][cb] bit c  <=>  IoU(sorted r, sorted cb*64+c) > thr, c later than r.
-__global__ void __launch_bounds__(64) mask_iou_matrix_kernel(const uint32_t* __restrict__ masks, int K, int H, int Wp,
-                                                             const int* __restrict__ order, const int* __restrict__ areas,
-                                                             const int4* __restrict__ tight, float thr,
-                                                             unsigned long long* __restrict__ matrix) {
+// grid (cb, rb) with cb >= rb: one CTA owns the 64 x 64 tile of sorted rows rb*64.. against sorted
+// columns cb*64...  matrix[r][cb] bit c  <=>  IoU(sorted r, sorted cb*64+c) > thr, c later than r.
+//  1. one thread per pair: tight-box overlap and the area / overlap bound decide most pairs
+//     without touching the masks (IoU is monotone in the intersection, so if even
+//     min(area_i, area_j, box overlap) cannot exceed thr the pair is clean);
+//  2. the undecided pairs are queued in shared memory and the 8 warps drain the queue, each
+//     pair's popc(a & b) over the intersection window spread across the 32 lanes — a pair costs
+//     (rows x words) / 32 steps instead of serialising in one thread next to idle neighbours.
+constexpr int kIouThreads = 256;
+
+__global__ void __launch_bounds__(kIouThreads) mask_iou_matrix_kernel(const uint32_t* __restrict__ masks, int K, int H, int Wp,
+                                                                      const int* __restrict__ order, const int* __restrict__ areas,
+                                                                      const int4* __restrict__ tight, float thr,
+                                                                      unsigned long long* __restrict__ matrix) {
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;
-  __shared__ int s_idx[64], s_area[64];
-  __shared__ int4 s_box[64];
-  const int cols = min(64, K - cb * 64);
-  if ((int)threadIdx.x < cols) {
-    const int j = order[cb * 64 + threadIdx.x];
-    s_idx[threadIdx.x] = j; s_area[threadIdx.x] = areas[j]; s_box[threadIdx.x] = tight[j];
+  __shared__ int r_idx[64], r_area[64], c_idx[64], c_area[64];
+  __shared__ int4 r_box[64], c_box[64];
+  __shared__ unsigned long long bits[64];
+  __shared__ unsigned short queue[64 * 64];
+  __shared__ int n_queue;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = min(64, K - rb * 64), cols = min(64, K - cb * 64);
+  if (tid < 64) {
+    bits[tid] = 0ull;
+    if (tid < rows) { const int i = order[rb * 64 + tid]; r_idx[tid] = i; r_area[tid] = areas[i]; r_box[tid] = tight[i]; }
+    if (tid < cols) { const int j = order[cb * 64 + tid]; c_idx[tid] = j; c_area[tid] = areas[j]; c_box[tid] = tight[j]; }
   }
+  if (tid == 0) n_queue = 0;
   __syncthreads();
-  const int r = rb * 64 + threadIdx.x;
-  if (r >= K) return;
-  const int i = order[r];
-  const int ai = areas[i];
-  const int4 bi = tight[i];
-  const uint32_t* mi = masks + (size_t)i * H * Wp;
-  const int nblk = (K + 63) >> 6;
-  unsigned long long bits = 0ull;
-  const int c0 = (rb == cb) ? (int)threadIdx.x + 1 : 0;
-  for (int c = c0; c < cols; ++c) {
-    const int4 bj = s_box[c];
+  for (int q = tid; q < 64 * 64; q += kIouThreads) {
+    const int r = q >> 6, c = q & 63;
+    if (r >= rows || c >= cols || (rb == cb && c <= r)) continue;
+    const int4 bi = r_box[r], bj = c_box[c];
     const int ix1 = max(bi.x, bj.x), iy1 = max(bi.y, bj.y), ix2 = min(bi.z, bj.z), iy2 = min(bi.w, bj.w);
     if (ix2 <= ix1 || iy2 <= iy1) continue;
-    const int aj = s_area[c];
+    const int ai = r_area[r], aj = c_area[c];
     const int ub = min(min(ai, aj), (ix2 - ix1) * (iy2 - iy1));
-    if (!(__fdiv_rn((float)ub, (float)(ai + aj - ub)) > thr)) continue;  // IoU is monotone in the intersection
-    const uint32_t* mj = masks + (size_t)s_idx[c] * H * Wp;
-    const int w1 = ix1 >> 5, w2 = (ix2 + 31) >> 5;
-    int inter = 0;
-    for (int y = iy1; y < iy2; ++y) {
-      const uint32_t* pi = mi + (size_t)y * Wp;
-      const uint32_t* pj = mj + (size_t)y * Wp;
-      for (int w = w1; w < w2; ++w) inter += __popc(__ldg(pi + w) & __ldg(pj + w));
-    }
-    if (__fdiv_rn((float)inter, (float)(ai + aj - inter)) > thr) bits |= 1ull << c;
+    if (!(__fdiv_rn((float)ub, (float)(ai + aj - ub)) > thr)) continue;
+    queue[atomicAdd(&n_queue, 1)] = (unsigned short)q;
   }
-  matrix[(size_t)r * nblk + cb] = bits;
+  __syncthreads();
+  const int nq = n_queue;
+  for (int e = warp; e < nq; e += kIouThreads / 32) {
+    const int q = queue[e], r = q >> 6, c = q & 63;
+    const int4 bi = r_box[r], bj = c_box[c];
+    const int ix1 = max(bi.x, bj.x), iy1 = max(bi.y, bj.y), ix2 = min(bi.z, bj.z), iy2 = min(bi.w, bj.w);
+    const int w1 = ix1 >> 5, nw = ((ix2 + 31) >> 5) - w1, nwin = nw * (iy2 - iy1);
+    const uint32_t* mi = masks + (size_t)r_idx[r] * H * Wp + (size_t)iy1 * Wp + w1;
+    const uint32_t* mj = masks + (size_t)c_idx[c] * H * Wp + (size_t)iy1 * Wp + w1;
+    int inter = 0;
+    for (int t = lane; t < nwin; t += 32) {
+      const int y = t / nw, w = t - y * nw;
+      inter += __popc(__ldg(mi + (size_t)y * Wp + w) & __ldg(mj + (size_t)y * Wp + w));
+    }
+    inter = warp_sum(inter);
+    if (lane == 0 && __fdiv_rn((float)inter, (float)(r_area[r] + c_area[c] - inter)) > thr)
+      atomicOr(&bits[r], 1ull << c);
+  }
+  __syncthreads();
+  const int nblk = (K + 63) >> 6;
+  if (tid < rows) matrix[(size_t)(rb * 64 + tid) * nblk + cb] = bits[tid];
 }
 
 // Box-IoU variant of the matrix (torchvision arithmetic), for large-K box NMS.
@@ -288,7 +307,7 @@ int launch_matrix_nms(const uint32_t* masks, const float4* boxes, int K, int H, 
   rank_sort_kernel<<<(K + 255) / 256, 256, 0, stream>>>(scores, K, order);
   const int nblk = (K + 63) >> 6;
   dim3 grid(nblk, nblk);
-  if (masks) mask_iou_matrix_kernel<<<grid, 64, 0, stream>>>(masks, K, H, Wp, order, areas, tight, thr, matrix);
+  if (masks) mask_iou_matrix_kernel<<<grid, kIouThreads, 0, stream>>>(masks, K, H, Wp, order, areas, tight, thr, matrix);
   else box_iou_matrix_kernel<<<grid, 64, 0, stream>>>(boxes, K, order, thr, matrix);
   greedy_scan_kernel<<<1, 32, nblk * sizeof(unsigned long long), stream>>>(matrix, K, order, keep, keep_count);
   return (int)cudaGetLastError();
