@@ -421,7 +421,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "images_per_rank": n_img, "proposals_per_image": n_prop,
                            "field_hw": [H, W], "chunk_images": chunk, "n_round": 50, "resize": "bilinear, antialias=False",
-                           "l2": "inputs (24.6 GB of fields per rank) exceed the 126 MB L2; no flush needed",
+                           "l2": f"inputs ({n_img * 4 * px * 4 / 1e9:.1f} GB of fields per rank) exceed the 126 MB L2; no flush needed",
                            "input_generation_s": round(t_gen, 1)},
                 "proposals_per_sec": images_per_s * n_prop, "detections": int(out.shape[0]),
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,

@@ -26,6 +26,13 @@ __device__ __forceinline__ const float* elem_ptr(const float* base, int idx) {
   asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(base));
   return r;
 }
+// base + byte offset: with the per-row base warp-uniform and the per-lane tap offsets precomputed in
+// bytes, a tap address is this single instruction
+__device__ __forceinline__ const float* byte_ptr(const float* base, unsigned off_bytes) {
+  const float* r;
+  asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off_bytes), "l"(base));
+  return r;
+}
 
 template <int LAYOUT>
 __device__ __forceinline__ int lane_column(int lane, int c) {
@@ -34,7 +41,7 @@ __device__ __forceinline__ int lane_column(int lane, int c) {
 
 // Column taps of this lane for the current window, shared by all channels.
 struct ColTaps {
-  int x0[4], x1[4];   // x1 = x0 + 1, or x0 again on the clamped right edge
+  unsigned x0[4], x1[4];   // BYTE offsets of the two taps inside a source row; x1 = x0 + 4, or x0 again on the clamped right edge
   float w0[4], w1[4];
   template <int LAYOUT>
   __device__ __forceinline__ void init(int lane, int in_w) {
@@ -42,7 +49,7 @@ struct ColTaps {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       AxisTap t = axis_tap(scale, lane_column<LAYOUT>(lane, c), in_w);
-      x0[c] = t.i0; x1[c] = t.i1; w0[c] = t.l0; w1[c] = t.l1;
+      x0[c] = 4u * (unsigned)t.i0; x1[c] = 4u * (unsigned)t.i1; w0[c] = t.l0; w1[c] = t.l1;
     }
   }
 };
@@ -63,12 +70,12 @@ struct PlaneRows {
     // 32-bit element offsets from the window origin, one address per tap.  Both taps of all four
     // columns are independent loads (no "v1 = v0 unless ..." dependency), so the eight requests of
     // a source row go out back to back and cost one memory round trip.
-    const int ro = y * stride;
+    const float* rowp = elem_ptr(origin, y * stride);   // warp-uniform
     float v0[4], v1[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      v0[c] = __ldg(elem_ptr(origin, ro + t.x0[c]));
-      v1[c] = __ldg(elem_ptr(origin, ro + t.x1[c]));
+      v0[c] = __ldg(byte_ptr(rowp, t.x0[c]));
+      v1[c] = __ldg(byte_ptr(rowp, t.x1[c]));
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c] = lerp_h(v0[c], v1[c], t.w0[c], t.w1[c]);
@@ -115,12 +122,12 @@ struct MultiPlaneRows {
     const int ro = y * stride;
     float v0[P][4], v1[P][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int i0 = ro + t.x0[c], i1 = ro + t.x1[c];
+    for (int p = 0; p < P; ++p) {
+      const float* rowp = elem_ptr(origin[p], ro);   // warp-uniform
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        v0[p][c] = __ldg(elem_ptr(origin[p], i0));
-        v1[p][c] = __ldg(elem_ptr(origin[p], i1));
+      for (int c = 0; c < 4; ++c) {
+        v0[p][c] = __ldg(byte_ptr(rowp, t.x0[c]));
+        v1[p][c] = __ldg(byte_ptr(rowp, t.x1[c]));
       }
     }
 #pragma unroll
