@@ -49,6 +49,16 @@ int unmore_existence_scores(const float* fields, int n_img, int C, int H, int W,
                             const void* boxes, int boxes_f64, const int* counts, int cap,
                             float* scores_out, void* ws, unmore_stream_t stream);
 
+/* The crop + Resize((128,128), BILINEAR) every stage starts with (object_reasoning.py:402-410,
+ * 314-321, 500-508; object_scoring.py:126-134) and get_prediction_with_proposals (:301-337 /
+ * object_scoring.py:112-157) as a stand-alone op: out [n_img, cap, n_channels, 128, 128] fp32 holds
+ * the resized crop of channel channels_host[k] (a HOST array of 1..4 indices) for every proposal,
+ * bit-identical to ATen's CPU bilinear kernel.  The fused kernels never materialise these tiles;
+ * this entry point exists for signature parity and for testing the resampler directly. */
+int unmore_crop_resize(const float* fields, int n_img, int C, int H, int W,
+                       const int* channels_host, int n_channels, const void* boxes, int boxes_f64,
+                       const int* counts, int cap, float* out, unmore_stream_t stream);
+
 /* center_reasoning — object_reasoning.py:525-580 with batch_erode (utils/misc.py:10-20) and
  * center_field_to_anti_center_map (object_reasoning.py:360-377) fused.
  * max_values_out [n_img, cap] fp64: amax of the masked anti-center map;
@@ -147,6 +157,12 @@ int unmore_score_and_rasterise(const float* fields, int n_img, int C, int H, int
                                int boxes_f64, const int* counts, int cap, float* scores_out,
                                float* tight_out, int* areas_out, uint32_t* masks_out,
                                unmore_stream_t stream);
+
+/* The mask resize of object_scoring.py:206-207 / 222-223 as a stand-alone op: masks [B, 128, 128] u8
+ * (non-zero = set) -> Resize((out_h, out_w), BILINEAR) + round half to even -> out [B, out_h, out_w]
+ * u8 {0,1}, in the exact arithmetic of the ATen CPU kernel that output size selects. */
+int unmore_mask_resize(const unsigned char* masks, int B, int H, int W, int out_h, int out_w,
+                       unsigned char* out, unmore_stream_t stream);
 
 /* main_object_scoring steps 7b-8 (object_scoring.py:244-266) + the post_process predicate
  * (post_process.py:61-74) for the detections kept by the second NMS, in keep order:

@@ -71,6 +71,51 @@ def test_update_bbox_from_tiles(golden_dir, dev, ops):
     assert np.array_equal(mx.cpu().numpy(), g["a10_tiles"].max(axis=(1, 2)))
 
 
+def test_crop_resize_bit_exact(golden_dir, dev, ops):
+    """a2 directly: the resized 128x128 crops against the reference's own Resize output, bit for bit
+    (up- and down-sampling, fractional boxes, image-edge and full-image windows), and through both
+    mirrors of get_prediction_with_proposals."""
+    from unmore_b200.object_reasoning import Object_Discovery
+    from unmore_b200.object_scoring import Object_Scoring
+    g = _load(golden_dir, "units.npz")
+    fields = synth.make_fields(3).to(dev)[None].contiguous()
+    boxes = torch.tensor(g["crop_boxes"], dtype=torch.float64, device=dev)[None].contiguous()
+    got = ops.crop_resize(fields, boxes, [0, 1, 2, 3])[0].cpu().numpy()
+    assert np.array_equal(got.view(np.int32), g["crop_out"].view(np.int32))
+    sdf, cen = Object_Discovery(device=dev).get_prediction_with_proposals(g["crop_boxes"], fields[0])
+    assert np.array_equal(sdf.cpu().numpy(), g["crop_out"][:, 0]) and np.array_equal(cen.cpu().numpy(), g["crop_out"][:, 1:3])
+    pred = Object_Scoring(device=dev).get_prediction_with_proposals(fields[0], g["crop_boxes"].tolist())
+    assert set(pred) == {"pred_boundary_fields", "pred_center_fields", "pred_existence_scores"}
+    assert np.array_equal(pred["pred_boundary_fields"].cpu().numpy(), g["crop_out"][:, 0])
+    assert_rel(pred["pred_existence_scores"].cpu().numpy(), g["crop_out"][:, 3].mean(axis=(1, 2)), "existence")
+    # fp32 boxes and ragged counts
+    counts = torch.tensor([3], dtype=torch.int32, device=dev)
+    got32 = ops.crop_resize(fields, boxes.float().contiguous(), [0], counts)[0].cpu().numpy()
+    b32 = g["crop_boxes"].astype(np.float32).astype(np.float64)
+    for k in range(3):
+        ref = O.crop_resize(synth.make_fields(3), b32[k])[0].numpy()
+        assert np.array_equal(got32[k, 0], ref)
+    assert not got32[3:].any()
+
+
+def test_mask_resize_round_half_even_golden(golden_dir, dev, ops):
+    """N2: Resize of int64 masks back to a box (object_scoring.py:206-207) against the reference's
+    output, sizes on both sides of ATen's h+w <= 128 kernel switch, dyadic sizes with exact 0.5 ties."""
+    g = _load(golden_dir, "units.npz")
+    masks = torch.tensor(g["n2_masks"], device=dev)
+    for k, (h, w) in enumerate(g["n2_sizes"]):
+        got = ops.mask_resize(masks, int(h), int(w)).cpu().numpy()
+        assert np.array_equal(got, g[f"n2_out_{k}"]), (h, w)
+    # many more sizes against the oracle (same ATen call the reference makes)
+    rng = np.random.default_rng(11)
+    for _ in range(25):
+        h, w = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        got = ops.mask_resize(masks, h, w).cpu().numpy()
+        for i in range(masks.shape[0]):
+            ref = O.resize_mask_to_box(torch.tensor(g["n2_masks"][i]).long(), h, w).numpy()
+            assert np.array_equal(got[i], ref), (h, w, i)
+
+
 def test_batch_erode_and_anti_center(golden_dir, dev, ops):
     from unmore_b200.utils.misc import batch_erode
     g = _load(golden_dir, "units.npz")

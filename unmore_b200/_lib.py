@@ -19,6 +19,7 @@ _d = C.c_double
 # name -> argtypes; every function returns int except where noted
 SIGNATURES = {
     "unmore_existence_scores": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],
+    "unmore_crop_resize": [_p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _i, _p, _p],
     "unmore_center_reasoning": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p],
     "unmore_boundary_refine": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p, _p, _p],
     "unmore_update_bbox_from_tiles": [_p, _i, _p, _p, _p],
@@ -29,6 +30,7 @@ SIGNATURES = {
     "unmore_anti_center_map": [_p, _i, _i, _i, _i, _p, _p],
     "unmore_box_nms_matrix": [_p, _p, _i, _f, _p, _p, _p, _p, _p],
     "unmore_score_and_rasterise": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
+    "unmore_mask_resize": [_p, _i, _i, _i, _i, _i, _p, _p],
     "unmore_final_scores": [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p],
     "unmore_sat_build": [_p, _i, _i, _i, _p, _p],
     "unmore_sat_build_fields": [_p, _i, _i, _i, _i, _p, _i, _p, _p],

@@ -94,6 +94,18 @@ int unmore_existence_scores(const float* fields, int n_img, int C, int H, int W,
   return cuda_fail(launch_existence(p, num_sms(), s), "existence_kernel");
 }
 
+int unmore_crop_resize(const float* fields, int n_img, int C, int H, int W, const int* channels_host, int n_channels,
+                       const void* boxes, int boxes_f64, const int* counts, int cap, float* out, unmore_stream_t stream) {
+  if (int e = check_fields(fields, n_img, C, H, W)) return e;
+  if (!boxes || !out || !channels_host || cap < 0 || n_channels < 1 || n_channels > 4)
+    return fail(UNMORE_E_INVALID, "unmore_crop_resize: bad argument (1..4 channels)");
+  for (int i = 0; i < n_channels; ++i)
+    if (channels_host[i] < 0 || channels_host[i] >= C) return fail(UNMORE_E_INVALID, "unmore_crop_resize: channel out of range");
+  return cuda_fail(launch_crop_resize(fields, n_img, C, H, W, channels_host, n_channels, boxes, boxes_f64, counts, cap, out,
+                                      (cudaStream_t)stream),
+                   "crop_resize_kernel");
+}
+
 int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W, int ch_sdf, int ch_center_row,
                             int ch_center_col, const void* boxes, int boxes_f64, const int* counts, int cap,
                             double center_score_max_thres, double* max_values_out, int* argmax_out,
@@ -229,6 +241,14 @@ int unmore_score_and_rasterise(const float* fields, int n_img, int C, int H, int
   p.scores = reinterpret_cast<float4*>(scores_out); p.tight = reinterpret_cast<float4*>(tight_out);
   p.areas = areas_out; p.masks = masks_out;
   return cuda_fail(launch_score(p, (cudaStream_t)stream), "score_kernel");
+}
+
+int unmore_mask_resize(const unsigned char* masks, int B, int H, int W, int out_h, int out_w, unsigned char* out,
+                       unmore_stream_t stream) {
+  if (B < 0 || out_h < 0 || out_w < 0 || (B > 0 && out_h > 0 && out_w > 0 && (!masks || !out)))
+    return fail(UNMORE_E_INVALID, "unmore_mask_resize: bad argument");
+  if (H != kCrop || W != kCrop) return fail(UNMORE_E_CAPACITY, "unmore_mask_resize: only 128x128 crops (got %dx%d)", H, W);
+  return cuda_fail(launch_mask_resize(masks, B, out_h, out_w, out, (cudaStream_t)stream), "mask_resize_kernel");
 }
 
 int unmore_final_scores(const float* scores, const float* tight, const int* areas, const int* keep,

@@ -32,6 +32,24 @@ __device__ __forceinline__ float bit_at(const uint32_t m[kCrop][4], int y, int x
   return (float)((m[y][x >> 5] >> (x & 31)) & 1u);
 }
 
+// One output pixel of Resize((oh, ow), BILINEAR) applied to a 128x128 {0,1} mask followed by
+// round-half-even (object_scoring.py:206-207): the bit is interp > 0.5, with the interpolation in the
+// exact arithmetic of whichever ATen CPU kernel the output size selects (common.cuh).
+__device__ __forceinline__ bool resized_mask_bit(const uint32_t m[kCrop][4], const AxisTap& ty, int x0, int x1, float w0,
+                                                 float w1, bool small_path) {
+  const float v00 = bit_at(m, ty.i0, x0), v01 = bit_at(m, ty.i0, x1);
+  const float v10 = bit_at(m, ty.i1, x0), v11 = bit_at(m, ty.i1, x1);
+  float val;
+  if (!small_path) {
+    val = lerp_v(lerp_h(v00, v01, w0, w1), lerp_h(v10, v11, w0, w1), ty.l0, ty.l1);
+  } else {
+    const float p00 = __fmul_rn(ty.l0, w0), p01 = __fmul_rn(ty.l0, w1);
+    const float p10 = __fmul_rn(ty.l1, w0), p11 = __fmul_rn(ty.l1, w1);
+    val = __fmaf_rn(p11, v11, __fmaf_rn(p10, v10, __fmaf_rn(p00, v00, __fmul_rn(p01, v01))));
+  }
+  return val > 0.5f;
+}
+
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(smem_raw);
@@ -130,17 +148,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
 #pragma unroll
         for (int mm = 0; mm < 2; ++mm) {
           const uint32_t (*m)[4] = mm == 0 ? sm.cmask : sm.bmask;
-          const float v00 = bit_at(m, ty.i0, x0), v01 = bit_at(m, ty.i0, x1);
-          const float v10 = bit_at(m, ty.i1, x0), v11 = bit_at(m, ty.i1, x1);
-          float val;
-          if (!small_path) {
-            val = lerp_v(lerp_h(v00, v01, w0, w1), lerp_h(v10, v11, w0, w1), ty.l0, ty.l1);
-          } else {
-            const float p00 = __fmul_rn(ty.l0, w0), p01 = __fmul_rn(ty.l0, w1);
-            const float p10 = __fmul_rn(ty.l1, w0), p11 = __fmul_rn(ty.l1, w1);
-            val = __fmaf_rn(p11, v11, __fmaf_rn(p10, v10, __fmaf_rn(p00, v00, __fmul_rn(p01, v01))));
-          }
-          on = on || (val > 0.5f);
+          on = on || resized_mask_bit(m, ty, x0, x1, w0, w1, small_path);
         }
         word |= (on ? 1u : 0u) << (x - xb);
       }
@@ -175,6 +183,35 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
     else p.tight[row] = make_float4(0.f, 0.f, 0.f, 0.f);
     p.areas[row] = sm.area;
   }
+}
+
+// Stand-alone form of the mask resize (unit parity with the reference's Resize on int64 masks):
+// masks [B,128,128] u8 -> out [B, oh, ow] u8.  One CTA per mask.
+__global__ void __launch_bounds__(256) mask_resize_kernel(const unsigned char* __restrict__ masks, int B, int oh, int ow,
+                                                          unsigned char* __restrict__ out) {
+  __shared__ uint32_t m[kCrop][4];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const unsigned char* src = masks + (size_t)b * kCrop * kCrop;
+  for (int w = tid; w < kCrop * 4; w += 256) {
+    uint32_t word = 0;
+    for (int k = 0; k < 32; ++k) word |= (src[w * 32 + k] ? 1u : 0u) << k;
+    m[w >> 2][w & 3] = word;
+  }
+  __syncthreads();
+  const float sx = __fdiv_rn((float)kCrop, (float)ow), sy = __fdiv_rn((float)kCrop, (float)oh);
+  const bool small_path = (oh + ow) <= 128;
+  unsigned char* o = out + (size_t)b * oh * ow;
+  for (int q = tid; q < oh * ow; q += 256) {
+    const int y = q / ow, x = q - y * ow;
+    const AxisTap ty = axis_tap(sy, y, kCrop), tx = axis_tap(sx, x, kCrop);
+    o[q] = resized_mask_bit(m, ty, tx.i0, tx.i1, tx.l0, tx.l1, small_path) ? 1 : 0;
+  }
+}
+
+int launch_mask_resize(const unsigned char* masks, int B, int oh, int ow, unsigned char* out, cudaStream_t stream) {
+  if (B <= 0 || oh <= 0 || ow <= 0) return 0;
+  mask_resize_kernel<<<B, 256, 0, stream>>>(masks, B, oh, ow, out);
+  return (int)cudaGetLastError();
 }
 
 int launch_score(const ScoreParams& p, cudaStream_t stream) {

@@ -46,6 +46,8 @@ struct ExistParams {
   float* scores;  // [n_img, cap]
 };
 int launch_existence(const ExistParams& p, int num_sms, cudaStream_t stream);
+int launch_crop_resize(const float* fields, int n_img, int C, int H, int W, const int* channels, int n_ch,
+                       const void* boxes, int boxes_f64, const int* counts, int cap, float* out, cudaStream_t stream);
 
 // ---- center.cu -----------------------------------------------------------------------
 #ifndef UNMORE_CC_CAP
@@ -129,6 +131,7 @@ struct ScoreParams {
   uint32_t* masks;     // nullable [n_img, cap, H, ceil(W/32)] packed union masks
 };
 int launch_score(const ScoreParams& p, cudaStream_t stream);
+int launch_mask_resize(const unsigned char* masks, int B, int oh, int ow, unsigned char* out, cudaStream_t stream);
 
 struct FinalParams {
   const float4* scores;  // [n_img, cap]

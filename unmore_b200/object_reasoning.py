@@ -77,6 +77,15 @@ class Object_Discovery:
         scores = ops.existence_scores(self._fields(image), boxes, ch=self.channels)
         return {"existence_scores": scores[0].cpu()}
 
+    # ---- a4 ---------------------------------------------------------------------------
+    def get_prediction_with_proposals(self, proposals, image):
+        """object_reasoning.py:301-337 (note the (proposals, image) order): the resized crops of the
+        boundary-distance and center fields, (sdf_maps [N,128,128], center_fields [N,2,128,128])."""
+        boxes = self._boxes(proposals)
+        ch = self.channels
+        crops = ops.crop_resize(self._fields(image), boxes, [ch.sdf, ch.center_row, ch.center_col])[0]
+        return crops[:, 0], crops[:, 1:3]
+
     # ---- a7 ---------------------------------------------------------------------------
     def center_reasoning(self, image, proposals) -> Dict[str, torch.Tensor]:
         """object_reasoning.py:525-580 — {'proposals_pass_singularity', 'splited_new_proposals'}

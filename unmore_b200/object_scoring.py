@@ -43,12 +43,15 @@ class Object_Scoring:
         return (f.unsqueeze(0) if f.dim() == 3 else f).contiguous()
 
     def get_prediction_with_proposals(self, image, proposals) -> Dict[str, torch.Tensor]:
-        """object_scoring.py:112-157 (note the (image, proposals) order).  The per-crop maps are
-        never materialised here; the dict carries the three reductions the caller takes of them."""
+        """object_scoring.py:112-157 (note the (image, proposals) order): the resized crops of the
+        boundary-distance and center fields and the per-crop existence score, under the reference's keys.
+        ``score_batch`` never materialises these tiles; this is the signature-parity / inspection form."""
         boxes = torch.as_tensor(np.asarray(proposals, dtype=np.float64)).reshape(1, -1, 4).to(self.device)
-        scores, _, _, _ = ops.score_and_rasterise(self._fields(image), boxes, ch=self.channels, want_masks=False)
-        return {"pred_existence_scores": scores[0, :, 0], "max_center_fields_norms": scores[0, :, 1],
-                "max_boundary_distance_values": scores[0, :, 2]}
+        ch = self.channels
+        f = self._fields(image)
+        crops = ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col])[0]
+        return {"pred_boundary_fields": crops[:, 0], "pred_center_fields": crops[:, 1:3],
+                "pred_existence_scores": ops.existence_scores(f, boxes, ch=ch)[0]}
 
     def score_batch(self, fields: torch.Tensor, boxes: torch.Tensor, counts: Optional[torch.Tensor] = None,
                     want_masks: bool = True):

@@ -62,10 +62,10 @@ _timer: Optional[StageTimer] = None
 LAUNCHES = 0  # kernels launched through the C ABI since import (gpu_launches in bench.py)
 
 # kernels per C-ABI call (memsets not counted); +1 when a counts prefix is built
-_KERNELS = {"unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
+_KERNELS = {"unmore_crop_resize": 1, "unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
             "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
             "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_connected_components": 1, "unmore_box_nms_matrix": 3,
-            "unmore_score_and_rasterise": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
+            "unmore_score_and_rasterise": 1, "unmore_mask_resize": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
             "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3, "unmore_mask_rle_counts": 1}
 
 
@@ -122,6 +122,20 @@ def existence_scores(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANNELS
     out = torch.zeros((n_img, cap), dtype=torch.float32, device=fields.device) if out is None else out
     _call("unmore_existence_scores", fields.data_ptr(), n_img, C, H, W, ch.exist, boxes.data_ptr(), f64,
               _ptr(counts), cap, out.data_ptr(), ws.data_ptr(), _stream(), counts=counts)
+    return out
+
+
+def crop_resize(fields, boxes, channels, counts=None):
+    """Resized crops [n_img, cap, len(channels), 128, 128] fp32 (a2 / a4 as a stand-alone op)."""
+    import ctypes
+    n_img, C, H, W = _check_fields(fields)
+    cap, f64 = _check_boxes(boxes, n_img)
+    _check_counts(counts, n_img)
+    ch = (ctypes.c_int * len(channels))(*[int(c) for c in channels])
+    out = torch.zeros((n_img, cap, len(channels), CROP, CROP), dtype=torch.float32, device=fields.device)
+    if cap:
+        _call("unmore_crop_resize", fields.data_ptr(), n_img, C, H, W, ctypes.cast(ch, ctypes.c_void_p), len(channels),
+              boxes.data_ptr(), f64, _ptr(counts), cap, out.data_ptr(), _stream())
     return out
 
 
@@ -187,11 +201,9 @@ def compact_boxes(inp, counts_in, mode, pred, thr=0.0, group=1, out=None, counts
                   out_dtype=None, append=False, want_index=False, group_counts=None, overflow=None):
     """Stable per-image selection; returns (out [n_img, cap_out, 4], counts_out [n_img], index or None)."""
     dev = inp.device
-    if group == 1:
-        n_img, cap_in = inp.shape[0], inp.shape[1]
-    else:
-        n_img, cap_in = inp.shape[0], inp.shape[1]
-        assert inp.shape[2] == group
+    n_img, cap_in = inp.shape[0], inp.shape[1]
+    if group != 1 and inp.shape[2] != group:
+        raise _lib.UnmoreError("compact_boxes: input must be [n_img, cap, group, 4]")
     out_dtype = out_dtype or inp.dtype
     if cap_out is None:
         cap_out = out.shape[1] if out is not None else cap_in * group
@@ -283,6 +295,16 @@ def score_and_rasterise(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANN
                   ch.exist, boxes.data_ptr(), f64, _ptr(counts), cap, scores.data_ptr(), tight.data_ptr(),
                   areas.data_ptr(), _ptr(masks), _stream())
     return scores, tight, areas, masks
+
+
+def mask_resize(masks_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """[B,128,128] u8 -> [B,out_h,out_w] u8: bilinear + round-half-even like the reference's Resize on int masks."""
+    m = masks_u8.contiguous()
+    B, H, W = m.shape
+    out = torch.zeros((B, out_h, out_w), dtype=torch.uint8, device=m.device)
+    if B and out_h and out_w:
+        _call("unmore_mask_resize", m.data_ptr(), B, H, W, int(out_h), int(out_w), out.data_ptr(), _stream())
+    return out
 
 
 def final_scores(scores, tight, areas, keep, keep_counts, existence_score_thres=0.5, center_score_thres=0.8,
