@@ -57,6 +57,44 @@ __device__ __forceinline__ float lerp_v(float t0, float t1, float h0, float h1) 
   return __fmaf_rn(t0, h0, __fmul_rn(t1, h1));
 }
 
+// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2): two IEEE round-to-nearest fp32 operations per
+// issue slot, bit-identical per element to the scalar __fmaf_rn / __fmul_rn / __fadd_rn forms.  ptxas folds a
+// pair built from one scalar twice into a broadcast operand (R.F32) and constants into immediates.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// the two lerp stages of the generic ATen kernel on a pair of pixels
+__device__ __forceinline__ f32x2 lerp_h2(f32x2 v0, f32x2 v1, f32x2 w0, f32x2 w1) { return fma2(v0, w0, mul2(v1, w1)); }
+__device__ __forceinline__ f32x2 lerp_v2(f32x2 t0, f32x2 t1, float h0, float h1) {
+  return fma2(t0, pk2(h0, h0), mul2(t1, pk2(h1, h1)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

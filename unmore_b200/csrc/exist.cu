@@ -32,12 +32,17 @@ __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const Exist
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
       double acc = 0.0;
-      float part = 0.f;
+      f32x2 part = pk2(0.f, 0.f);   // two fp32 partial sums per lane, flushed to fp64 every 8 rows
       for (int i = 0; i < kCrop; ++i) {
-        float v[4];
-        plane.row(taps, axis_tap(scale_y, i, in_h), v);
-        part += (v[0] + v[1]) + (v[2] + v[3]);
-        if ((i & 7) == 7) { acc += (double)part; part = 0.f; }
+        f32x2 v[2];
+        plane.row2(taps, axis_tap(scale_y, i, in_h), v);
+        part = add2(part, add2(v[0], v[1]));
+        if ((i & 7) == 7) {
+          float lo, hi;
+          upk2(part, lo, hi);
+          acc += (double)(lo + hi);
+          part = pk2(0.f, 0.f);
+        }
       }
       acc = warp_sum(acc);
       score = (float)(acc * (1.0 / (kCrop * kCrop)));

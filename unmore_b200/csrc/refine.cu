@@ -35,20 +35,21 @@ __device__ __forceinline__ float soft_fg(float s) {
 
 struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
   const float* tile;
-  __device__ __forceinline__ void row(int lane, int i, float out[4]) const {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
-    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  float4 pend;
+  __device__ __forceinline__ void issue(int lane, int i) {
+    pend = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
   }
+  __device__ __forceinline__ void finish(f32x2 out[2]) { out[0] = pk2(pend.x, pend.y); out[1] = pk2(pend.z, pend.w); }
 };
 
 struct CropRows {  // crop window of the boundary-distance channel, resampled on the fly
   ColTaps taps;
   PlaneRows plane;
+  PlaneRows::Fetch pend;
   float scale_y;
   int in_h;
-  __device__ __forceinline__ void row(int /*lane*/, int i, float out[4]) {
-    plane.row(taps, axis_tap(scale_y, i, in_h), out);
-  }
+  __device__ __forceinline__ void issue(int /*lane*/, int i) { plane.issue(taps, axis_tap(scale_y, i, in_h), pend); }
+  __device__ __forceinline__ void finish(f32x2 out[2]) { plane.finish(taps, pend, out); }
 };
 
 // Per-warp scratch: S[i][0] and S[i][126] for i in [0,127) so the border pass needs no resample.
@@ -62,68 +63,96 @@ struct Deltas {
   float dx1, dy1, dx2, dy2;
 };
 
-// a10 on one proposal.  `src.row(lane, i, out)` yields S[i][4*lane .. 4*lane+3].
+// a10 on one proposal.  `src.issue(lane, i)` / `src.finish(out)` yield S[i][4*lane .. 4*lane+3] as two packed pairs.
+// The per-pixel formula runs on pairs (FFMA2 / FMUL2 / FADD2): one issue slot per two pixels for
+// everything but the three MUFU evaluations and the horizontal difference.
 template <class RowSrc>
 __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, int lane) {
-  float ra[4], rb[4], top[4], bot[4];
-  src.row(lane, 0, ra);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) top[c] = bot[c] = ra[c];
-  float mx = fmaxf(fmaxf(ra[0], ra[1]), fmaxf(ra[2], ra[3]));
+  f32x2 ra[2], rb[2];
+  float top[4], bot[4];
+  src.issue(lane, 0);
+  src.finish(ra);
+  src.issue(lane, 1);
+  upk2(ra[0], top[0], top[1]);
+  upk2(ra[1], top[2], top[3]);
+  float mx = fmaxf(fmaxf(top[0], top[1]), fmaxf(top[2], top[3]));
   double dA = 0.0, dAg = 0.0, dB = 0.0, dBg = 0.0;
-  float fA = 0.f, fAg = 0.f, fB = 0.f, fBg = 0.f;
+  const f32x2 kZero2 = pk2(0.f, 0.f), kOne2 = pk2(1.f, 1.f);
+  f32x2 fA = kZero2, fAg = kZero2, fB = kZero2, fBg = kZero2;
+  // column 127 (second pixel of the upper pair of lane 31) is outside the 127x127 region: its foreground
+  // and background weights are forced to zero by a per-lane constant pair
+  const f32x2 keep_hi = pk2(1.f, lane < 31 ? 1.f : 0.f), neg_keep_hi = pk2(-1.f, lane < 31 ? -1.f : -0.f);
   // One output row of the 127x127 region: cur = S[i][.], nxt = S[i+1][.].
-  auto process = [&](const float (&cur)[4], const float (&nxt)[4], int i) {
-    const float right = __shfl_down_sync(kFullMask, cur[0], 1);  // S[i][4l+4]
-    if (lane == 0) cols.left[i] = cur[0];     // column 0
-    if (lane == 31) cols.right[i] = cur[2];   // column 126
-    // the four pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a);
-    // stage them so the MUFU latencies overlap instead of serialising pixel after pixel
-    float t[4], u[4], g[4], a[4];
+  auto process = [&](const f32x2 (&cur)[2], const f32x2 (&nxt)[2], int i) {
+    float c0, c1, c2, c3, n0, n1, n2, n3;
+    upk2(cur[0], c0, c1); upk2(cur[1], c2, c3);
+    upk2(nxt[0], n0, n1); upk2(nxt[1], n2, n3);
+    const float right = __shfl_down_sync(kFullMask, c0, 1);  // S[i][4l+4]
+    if (lane == 0) cols.left[i] = c0;     // column 0
+    if (lane == 31) cols.right[i] = c2;   // column 126
+    const f32x2 dx[2] = {pk2(c1 - c0, c2 - c1), pk2(c3 - c2, right - c3)};
+    // the pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a); stage them so the
+    // MUFU latencies overlap instead of serialising pixel after pixel
+    f32x2 t[2], u[2], g[2], a[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float s = cur[c];
-      const float dxv = (c < 3 ? cur[c + 1] : right) - s;
-      const float dyv = nxt[c] - s;
-      t[c] = fmaf(dyv, dyv, dxv * dxv);
-      u[c] = -1.4426950408889634f * s;
+    for (int h = 0; h < 2; ++h) {
+      const f32x2 dy = sub2(nxt[h], cur[h]);
+      t[h] = fma2(dy, dy, mul2(dx[h], dx[h]));
+      u[h] = mul2(cur[h], pk2(-1.4426950408889634f, -1.4426950408889634f));
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { u[c] = ex2_approx(u[c]); g[c] = sqrt_approx(t[c]); }  // ||grad|| only feeds the averaged sums
-#pragma unroll
-    for (int c = 0; c < 4; ++c) u[c] = 1.f + u[c];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) a[c] = rcp_approx(u[c]);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float b = 1.f - a[c];
-      if ((c < 3) || (lane < 31)) {  // column 127 is outside the 127x127 region
-        fA += a[c];
-        fAg = fmaf(a[c], g[c], fAg);
-        fB += b;
-        fBg = fmaf(b, g[c], fBg);
-      }
-      mx = fmaxf(mx, nxt[c]);
+    for (int h = 0; h < 2; ++h) {   // ||grad|| only feeds the averaged sums
+      float tl, th, ul, uh;
+      upk2(t[h], tl, th); upk2(u[h], ul, uh);
+      u[h] = pk2(ex2_approx(ul), ex2_approx(uh));
+      g[h] = pk2(sqrt_approx(tl), sqrt_approx(th));
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) u[h] = add2(u[h], kOne2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float ul, uh;
+      upk2(u[h], ul, uh);
+      a[h] = pk2(rcp_approx(ul), rcp_approx(uh));
+    }
+    {
+      const f32x2 b = sub2(kOne2, a[0]);
+      fA = add2(fA, a[0]); fAg = fma2(a[0], g[0], fAg);
+      fB = add2(fB, b);    fBg = fma2(b, g[0], fBg);
+    }
+    {
+      const f32x2 am = mul2(a[1], keep_hi);
+      const f32x2 b = fma2(a[1], neg_keep_hi, keep_hi);   // 1 - a, or 0 for column 127
+      fA = add2(fA, am); fAg = fma2(am, g[1], fAg);
+      fB = add2(fB, b);  fBg = fma2(b, g[1], fBg);
+    }
+    mx = fmaxf(fmaxf(mx, fmaxf(n0, n1)), fmaxf(n2, n3));
   };
-  // fp32 partial sums are flushed into fp64 every 8 rows (32 px per lane): keeps the
+  // fp32 partial sums (two per lane) are flushed into fp64 every 8 rows (16 px per partial): keeps the
   // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
   auto flush = [&]() {
-    dA += (double)fA; dAg += (double)fAg; dB += (double)fB; dBg += (double)fBg;
-    fA = fAg = fB = fBg = 0.f;
+    float lo, hi;
+    upk2(fA, lo, hi); dA += (double)(lo + hi);
+    upk2(fAg, lo, hi); dAg += (double)(lo + hi);
+    upk2(fB, lo, hi); dB += (double)(lo + hi);
+    upk2(fBg, lo, hi); dBg += (double)(lo + hi);
+    fA = fAg = fB = fBg = kZero2;
   };
-  // rows ping-pong between ra / rb so no register copies are needed
+  // rows ping-pong between ra / rb so no register copies are needed; the taps of row i+2 are requested
+  // before row i is processed and collected after it
   for (int i = 0; i < kCrop - 2; i += 2) {
-    src.row(lane, i + 1, rb);
+    src.finish(rb);            // row i+1
+    src.issue(lane, i + 2);
     process(ra, rb, i);
-    src.row(lane, i + 2, ra);
+    src.finish(ra);            // row i+2
+    src.issue(lane, i + 3);    // i + 3 <= 127
     process(rb, ra, i + 1);
     if ((i & 7) == 6) flush();
   }
-  // i = 126: ra holds row 126
-#pragma unroll
-  for (int c = 0; c < 4; ++c) bot[c] = ra[c];
-  src.row(lane, kCrop - 1, rb);
+  // i = 126: ra holds row 126, row 127 is in flight
+  upk2(ra[0], bot[0], bot[1]);
+  upk2(ra[1], bot[2], bot[3]);
+  src.finish(rb);
   process(ra, rb, kCrop - 2);
   flush();
   Deltas d;
@@ -222,10 +251,13 @@ __device__ __forceinline__ int one_round(const RefineParams& p, const float* pla
   return label;
 }
 
-constexpr int kRefineWarps = 8;
+#ifndef UNMORE_REFINE_WARPS
+#define UNMORE_REFINE_WARPS 8
+#endif
+constexpr int kRefineWarps = UNMORE_REFINE_WARPS;
 
 #ifndef UNMORE_REFINE_MINBLOCKS
-#define UNMORE_REFINE_MINBLOCKS 3
+#define UNMORE_REFINE_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) refine_kernel(const RefineParams p) {
   __shared__ BorderCols cols_all[kRefineWarps];

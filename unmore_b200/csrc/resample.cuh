@@ -39,34 +39,39 @@ __device__ __forceinline__ int lane_column(int lane, int c) {
   return LAYOUT == kStrided ? lane + 32 * c : 4 * lane + c;
 }
 
-// Column taps of this lane for the current window, shared by all channels.
+// Column taps of this lane for the current window, shared by all channels.  Weights are kept as packed
+// pairs (columns c = 0,1 and c = 2,3 of the lane) so the horizontal stage is two FMUL2 + two FFMA2.
 struct ColTaps {
   unsigned x0[4], x1[4];   // BYTE offsets of the two taps inside a source row; x1 = x0 + 4, or x0 again on the clamped right edge
-  float w0[4], w1[4];
+  f32x2 w0[2], w1[2];
   template <int LAYOUT>
   __device__ __forceinline__ void init(int lane, int in_w) {
     const float scale = __fdiv_rn((float)in_w, (float)kCrop);
+    float l0[4], l1[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       AxisTap t = axis_tap(scale, lane_column<LAYOUT>(lane, c), in_w);
-      x0[c] = 4u * (unsigned)t.i0; x1[c] = 4u * (unsigned)t.i1; w0[c] = t.l0; w1[c] = t.l1;
+      x0[c] = 4u * (unsigned)t.i0; x1[c] = 4u * (unsigned)t.i1; l0[c] = t.l0; l1[c] = t.l1;
     }
+    w0[0] = pk2(l0[0], l0[1]); w0[1] = pk2(l0[2], l0[3]);
+    w1[0] = pk2(l1[0], l1[1]); w1[1] = pk2(l1[2], l1[3]);
   }
 };
 
-// One channel plane of one window, with a two-row cache of horizontally interpolated rows.
+// One channel plane of one window, with a two-row cache of horizontally interpolated rows
+// (held as packed pairs: element h = columns 2h, 2h+1 of the lane).
 struct PlaneRows {
   const float* origin;  // &plane[y1 * W + x1]
   int stride;           // W
   int cy0, cy1;         // source rows held in ra / rb (-1: none)
-  float ra[4], rb[4];
+  f32x2 ra[2], rb[2];
 
   __device__ __forceinline__ void init(const float* plane, int W, const Window& win) {
     origin = plane + (size_t)win.y1 * W + win.x1;
     stride = W;
     cy0 = cy1 = -1;
   }
-  __device__ __forceinline__ void hrow(const ColTaps& t, int y, float out[4]) const {
+  __device__ __forceinline__ void hrow(const ColTaps& t, int y, f32x2 out[2]) const {
     // 32-bit element offsets from the window origin, one address per tap.  Both taps of all four
     // columns are independent loads (no "v1 = v0 unless ..." dependency), so the eight requests of
     // a source row go out back to back and cost one memory round trip.
@@ -78,27 +83,92 @@ struct PlaneRows {
       v1[c] = __ldg(byte_ptr(rowp, t.x1[c]));
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = lerp_h(v0[c], v1[c], t.w0[c], t.w1[c]);
+    for (int h = 0; h < 2; ++h)
+      out[h] = lerp_h2(pk2(v0[2 * h], v0[2 * h + 1]), pk2(v1[2 * h], v1[2 * h + 1]), t.w0[h], t.w1[h]);
   }
-  // S[i][lane_column(lane, c)], c = 0..3, for the output row whose vertical tap is `v`
-  __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[4]) {
+  // S[i][lane_column(lane, 2h)], S[i][lane_column(lane, 2h+1)] packed in out[h], for the output row whose vertical tap is `v`
+  __device__ __forceinline__ void row2(const ColTaps& t, const AxisTap& v, f32x2 out[2]) {
     if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
       if (v.i0 == cy1) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ra[c] = rb[c];
+        ra[0] = rb[0]; ra[1] = rb[1];
       } else {
         hrow(t, v.i0, ra);
       }
       if (v.i1 == v.i0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rb[c] = ra[c];
+        rb[0] = ra[0]; rb[1] = ra[1];
       } else {
         hrow(t, v.i1, rb);
       }
       cy0 = v.i0; cy1 = v.i1;
     }
+    out[0] = lerp_v2(ra[0], rb[0], v.l0, v.l1);
+    out[1] = lerp_v2(ra[1], rb[1], v.l0, v.l1);
+  }
+  __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[4]) {
+    f32x2 o[2];
+    row2(t, v, o);
+    upk2(o[0], out[0], out[1]);
+    upk2(o[1], out[2], out[3]);
+  }
+
+  // ---- split-phase form: issue() starts the tap loads an output row still needs (none, one or two
+  // source rows; both rows' sixteen requests go out together), finish() turns them into the row.  The
+  // caller puts a whole row of arithmetic between the two, so the L1/L2 round trip of row i+1 is hidden
+  // behind the work on row i.  The (cy0, cy1) bookkeeping depends only on tap indices, never on data, so
+  // it can run ahead at issue time.
+  struct Fetch {
+    int kind;   // 0 cache hit; 1 shift + new lower row (B); 2 both rows new (A, B); 3 one new row twice (A); 4 shift, clamped
+    float l0, l1;
+    float a0[4], a1[4], b0[4], b1[4];
+  };
+  __device__ __forceinline__ void load_taps(const ColTaps& t, int y, float v0[4], float v1[4]) const {
+    const float* rowp = elem_ptr(origin, y * stride);   // warp-uniform
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = lerp_v(ra[c], rb[c], v.l0, v.l1);
+    for (int c = 0; c < 4; ++c) {
+      v0[c] = __ldg(byte_ptr(rowp, t.x0[c]));
+      v1[c] = __ldg(byte_ptr(rowp, t.x1[c]));
+    }
+  }
+  __device__ __forceinline__ void issue(const ColTaps& t, const AxisTap& v, Fetch& f) {
+    f.l0 = v.l0; f.l1 = v.l1;
+    if (v.i0 == cy0 && v.i1 == cy1) { f.kind = 0; return; }   // all branches warp-uniform
+    if (v.i0 == cy1) {
+      if (v.i1 == v.i0) {
+        f.kind = 4;
+      } else {
+        f.kind = 1;
+        load_taps(t, v.i1, f.b0, f.b1);
+      }
+    } else {
+      load_taps(t, v.i0, f.a0, f.a1);
+      if (v.i1 == v.i0) {
+        f.kind = 3;
+      } else {
+        f.kind = 2;
+        load_taps(t, v.i1, f.b0, f.b1);
+      }
+    }
+    cy0 = v.i0; cy1 = v.i1;
+  }
+  __device__ __forceinline__ void finish(const ColTaps& t, const Fetch& f, f32x2 out[2]) {
+    if (f.kind != 0) {
+      if (f.kind == 1 || f.kind == 4) {
+        ra[0] = rb[0]; ra[1] = rb[1];
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          ra[h] = lerp_h2(pk2(f.a0[2 * h], f.a0[2 * h + 1]), pk2(f.a1[2 * h], f.a1[2 * h + 1]), t.w0[h], t.w1[h]);
+      }
+      if (f.kind == 1 || f.kind == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          rb[h] = lerp_h2(pk2(f.b0[2 * h], f.b0[2 * h + 1]), pk2(f.b1[2 * h], f.b1[2 * h + 1]), t.w0[h], t.w1[h]);
+      } else {
+        rb[0] = ra[0]; rb[1] = ra[1];
+      }
+    }
+    out[0] = lerp_v2(ra[0], rb[0], f.l0, f.l1);
+    out[1] = lerp_v2(ra[1], rb[1], f.l0, f.l1);
   }
 };
 
@@ -110,7 +180,7 @@ struct MultiPlaneRows {
   const float* origin[P];
   int stride;
   int cy0, cy1;
-  float ra[P][4], rb[P][4];
+  f32x2 ra[P][2], rb[P][2];
 
   __device__ __forceinline__ void init(const float* const planes[P], int W, const Window& win) {
 #pragma unroll
@@ -118,7 +188,7 @@ struct MultiPlaneRows {
     stride = W;
     cy0 = cy1 = -1;
   }
-  __device__ __forceinline__ void hrows(const ColTaps& t, int y, float out[P][4]) const {
+  __device__ __forceinline__ void hrows(const ColTaps& t, int y, f32x2 out[P][2]) const {
     const int ro = y * stride;
     float v0[P][4], v1[P][4];
 #pragma unroll
@@ -133,23 +203,20 @@ struct MultiPlaneRows {
 #pragma unroll
     for (int p = 0; p < P; ++p)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) out[p][c] = lerp_h(v0[p][c], v1[p][c], t.w0[c], t.w1[c]);
+      for (int h = 0; h < 2; ++h)
+        out[p][h] = lerp_h2(pk2(v0[p][2 * h], v0[p][2 * h + 1]), pk2(v1[p][2 * h], v1[p][2 * h + 1]), t.w0[h], t.w1[h]);
   }
   __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float out[P][4]) {
     if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
       if (v.i0 == cy1) {
 #pragma unroll
-        for (int p = 0; p < P; ++p)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) ra[p][c] = rb[p][c];
+        for (int p = 0; p < P; ++p) { ra[p][0] = rb[p][0]; ra[p][1] = rb[p][1]; }
       } else {
         hrows(t, v.i0, ra);
       }
       if (v.i1 == v.i0) {
 #pragma unroll
-        for (int p = 0; p < P; ++p)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) rb[p][c] = ra[p][c];
+        for (int p = 0; p < P; ++p) { rb[p][0] = ra[p][0]; rb[p][1] = ra[p][1]; }
       } else {
         hrows(t, v.i1, rb);
       }
@@ -158,7 +225,10 @@ struct MultiPlaneRows {
 #pragma unroll
     for (int p = 0; p < P; ++p)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) out[p][c] = lerp_v(ra[p][c], rb[p][c], v.l0, v.l1);
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 o = lerp_v2(ra[p][h], rb[p][h], v.l0, v.l1);
+        upk2(o, out[p][2 * h], out[p][2 * h + 1]);
+      }
   }
 };
 
