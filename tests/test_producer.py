@@ -103,3 +103,15 @@ def test_field_producer_stack_layout():
         pred = small(x)
     assert torch.equal(out[:, 0:1], pred["sdf_maps"]) and torch.equal(out[:, 1:3], pred["center_fields"])
     assert torch.equal(out[:, 3:4], fp.binary_classifier_model.dense(x))
+
+
+def test_calibrated_random_init_gives_non_degenerate_fields():
+    torch.manual_seed(7)
+    fp = P.FieldProducer(P.ObjectnessNet(vit=_small_vit()).eval(), P.Binary_Classifier().eval())
+    x = torch.rand(1, 3, 96, 128)
+    fp.calibrate_random_init(x)
+    out = fp(x)
+    sdf, cen, ex = out[0, 0], out[0, 1:3], out[0, 3]
+    assert float(sdf.abs().max()) <= 1.0 and 0.3 < float(torch.atanh(sdf.clamp(-0.999, 0.999)).std()) < 1.5
+    assert 0.3 < float(cen.std()) < 1.0
+    assert 0.05 < float(ex.min()) and float(ex.max()) < 0.99 and float(ex.std()) > 0.02

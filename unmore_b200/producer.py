@@ -339,3 +339,40 @@ class FieldProducer(nn.Module):
         out[:, 1:3].copy_(pred["center_fields"])
         out[:, 3:4].copy_(exist)
         return out
+
+    @torch.no_grad()
+    def calibrate_random_init(self, images: torch.Tensor, sdf_std: float = 1.0, center_std: float = 0.6,
+                              exist_logit_std: float = 2.0) -> None:
+        """Random-init nets put out ~1e-2 everywhere (sdf ~ 0 -> every proposal dies in round 0), which
+        would make configs[0]/[4] a degenerate workload.  This rescales the LAST convolution of each head
+        (and the classifier head) so that, on ``images``, the boundary head's pre-activation has standard
+        deviation ``sdf_std``, the center field ``center_std`` and the existence logit ``exist_logit_std``:
+        still random weights of the reference architecture, but fields with objects-sized structure in
+        them.  Benchmarks that use it say so in their ``config``."""
+        feat = self.objectness_model.backbone(images)
+
+        def rescale(head: nn.Sequential, target: float):
+            convs = [m for m in head if isinstance(m, nn.Conv2d)]
+            pre = feat
+            for m in head:
+                if m is convs[-1]:
+                    break
+                pre = m(pre)
+            y = F.conv2d(pre, convs[-1].weight)       # without bias
+            mean = y.mean(dim=(0, 2, 3))
+            s = float((y - mean[None, :, None, None]).std())
+            if s > 0:
+                convs[-1].weight.mul_(target / s)
+                convs[-1].bias.copy_(-mean * (target / s))   # centred: random features carry a large constant part
+
+        rescale(self.objectness_model.sdf_prediction_head, sdf_std)
+        rescale(self.objectness_model.center_field_prediction_head, center_std)
+        clf = self.binary_classifier_model
+        f = clf._trunk(images)
+        logits = F.conv2d(f, clf.classifier_backbone.fc.weight[:, :, None, None], clf.classifier_backbone.fc.bias)
+        h = clf.binary_classification_head
+        y = F.conv2d(logits, h.weight[:, :, None, None])
+        s = float(y.std())
+        if s > 0:
+            h.weight.mul_(exist_logit_std / s)
+            h.bias.fill_(float(-(y * (exist_logit_std / s)).mean()) + 0.5)   # centred, slightly positive
