@@ -126,18 +126,14 @@ template <bool ANALYZE_CC>
 __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CenterSmem& sm = *reinterpret_cast<CenterSmem*>(smem_raw);
-  __shared__ int s_id[2];
+  __shared__ int s_id;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = worklist_total(p.work);
-  if (tid == 0) s_id[0] = atomicAdd(p.work.counter, 1);
-  __syncthreads();
-  for (int it = 0;; ++it) {
-    const int id = s_id[it & 1];
+  for (;;) {
+    if (tid == 0) s_id = atomicAdd(p.work.counter, 1);
+    __syncthreads();
+    const int id = s_id;
     if (id >= total) break;
-    // the next work item is requested now and published at the end of this proposal, so the atomic's
-    // round trip to L2 hides behind ~50k cycles of work instead of idling the CTA
-    int next_id = 0;
-    if (tid == 0) next_id = atomicAdd(p.work.counter, 1);
     int img, k;
     worklist_locate(p.work, id, img, k);
     const size_t row = (size_t)img * p.work.cap + k;
@@ -373,8 +369,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       }
       if (tid == 0) p.cc_counts[row] = (unsigned char)(n_comp >= 2 ? min(n_comp, kCcCap) : 0);
     }
-    if (tid == 0) s_id[(it + 1) & 1] = next_id;
-    __syncthreads();  // publishes the next id; shared tiles are reused by the next proposal
+    __syncthreads();  // s_id and shared tiles are reused by the next proposal
   }
 }
 

@@ -14,11 +14,9 @@ constexpr int kExistWarps = 8;
 __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const ExistParams p) {
   const int lane = threadIdx.x & 31;
   const int total = worklist_total(p.work);
-  int id = worklist_next_warp(p.work);
-  while (id < total) {
-    // request the next item now (lane 0), read it after this proposal: the atomic's latency is hidden
-    int next_id = 0;
-    if (lane == 0) next_id = atomicAdd(p.work.counter, 1);
+  for (;;) {
+    const int id = worklist_next_warp(p.work);
+    if (id >= total) break;
     int img, k;
     worklist_locate(p.work, id, img, k);
     const size_t row = (size_t)img * p.work.cap + k;
@@ -50,7 +48,6 @@ __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const Exist
       score = (float)(acc * (1.0 / (kCrop * kCrop)));
     }
     if (lane == 0) p.scores[row] = score;
-    id = __shfl_sync(kFullMask, next_id, 0);
   }
 }
 
