@@ -52,10 +52,15 @@ struct CropRows {  // crop window of the boundary-distance channel, resampled on
   __device__ __forceinline__ void finish(f32x2 out[2]) { plane.finish(taps, pend, out); }
 };
 
-// Per-warp scratch: S[i][0] and S[i][126] for i in [0,127) so the border pass needs no resample.
+// Per-warp scratch (3 KB): the four borders of the resampled tile — S[i][0], S[i][126] for i in [0,127),
+// S[0][j], S[126][j] — so the border pass needs no resample, and the fp64 running sums of each lane.
+// Keeping these out of registers is what lets the split-phase row fetch fit the register budget.
 struct BorderCols {
   float left[kCrop];
   float right[kCrop];
+  float top[kCrop];
+  float bot[kCrop];
+  double acc[4][32];   // sum A, sum A*g, sum B, sum B*g per lane
 };
 
 struct Deltas {
@@ -69,19 +74,22 @@ struct Deltas {
 template <class RowSrc>
 __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, int lane) {
   f32x2 ra[2], rb[2];
-  float top[4], bot[4];
   src.issue(lane, 0);
   src.finish(ra);
   src.issue(lane, 1);
-  upk2(ra[0], top[0], top[1]);
-  upk2(ra[1], top[2], top[3]);
-  float mx = fmaxf(fmaxf(top[0], top[1]), fmaxf(top[2], top[3]));
-  double dA = 0.0, dAg = 0.0, dB = 0.0, dBg = 0.0;
+  float mx;
+  {
+    float t0, t1, t2, t3;
+    upk2(ra[0], t0, t1);
+    upk2(ra[1], t2, t3);
+    mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+    *reinterpret_cast<float4*>(&cols.top[4 * lane]) = make_float4(t0, t1, t2, t3);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cols.acc[k][lane] = 0.0;
   const f32x2 kZero2 = pk2(0.f, 0.f), kOne2 = pk2(1.f, 1.f);
   f32x2 fA = kZero2, fAg = kZero2, fB = kZero2, fBg = kZero2;
-  // column 127 (second pixel of the upper pair of lane 31) is outside the 127x127 region: its foreground
-  // and background weights are forced to zero by a per-lane constant pair
-  const f32x2 keep_hi = pk2(1.f, lane < 31 ? 1.f : 0.f), neg_keep_hi = pk2(-1.f, lane < 31 ? -1.f : -0.f);
+  const bool last_lane = lane == 31;
   // One output row of the 127x127 region: cur = S[i][.], nxt = S[i+1][.].
   auto process = [&](const f32x2 (&cur)[2], const f32x2 (&nxt)[2], int i) {
     float c0, c1, c2, c3, n0, n1, n2, n3;
@@ -89,7 +97,7 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     upk2(nxt[0], n0, n1); upk2(nxt[1], n2, n3);
     const float right = __shfl_down_sync(kFullMask, c0, 1);  // S[i][4l+4]
     if (lane == 0) cols.left[i] = c0;     // column 0
-    if (lane == 31) cols.right[i] = c2;   // column 126
+    if (last_lane) cols.right[i] = c2;    // column 126
     const f32x2 dx[2] = {pk2(c1 - c0, c2 - c1), pk2(c3 - c2, right - c3)};
     // the pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a); stage them so the
     // MUFU latencies overlap instead of serialising pixel after pixel
@@ -121,21 +129,25 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
       fB = add2(fB, b);    fBg = fma2(b, g[0], fBg);
     }
     {
-      const f32x2 am = mul2(a[1], keep_hi);
-      const f32x2 b = fma2(a[1], neg_keep_hi, keep_hi);   // 1 - a, or 0 for column 127
+      // column 127 (second pixel of the upper pair of lane 31) is outside the 127x127 region: its
+      // foreground and background weights are forced to zero
+      float al, ah, bl, bh;
+      upk2(a[1], al, ah);
+      upk2(sub2(kOne2, a[1]), bl, bh);
+      const f32x2 am = pk2(al, last_lane ? 0.f : ah), b = pk2(bl, last_lane ? 0.f : bh);
       fA = add2(fA, am); fAg = fma2(am, g[1], fAg);
       fB = add2(fB, b);  fBg = fma2(b, g[1], fBg);
     }
     mx = fmaxf(fmaxf(mx, fmaxf(n0, n1)), fmaxf(n2, n3));
   };
-  // fp32 partial sums (two per lane) are flushed into fp64 every 8 rows (16 px per partial): keeps the
-  // 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
+  // fp32 partial sums (two per lane) are flushed into the lane's fp64 sums every 8 rows (16 px per partial):
+  // keeps the 16129-term sums within ~1e-7 of exact without paying an F2F+DADD per pixel
   auto flush = [&]() {
     float lo, hi;
-    upk2(fA, lo, hi); dA += (double)(lo + hi);
-    upk2(fAg, lo, hi); dAg += (double)(lo + hi);
-    upk2(fB, lo, hi); dB += (double)(lo + hi);
-    upk2(fBg, lo, hi); dBg += (double)(lo + hi);
+    upk2(fA, lo, hi); cols.acc[0][lane] += (double)(lo + hi);
+    upk2(fAg, lo, hi); cols.acc[1][lane] += (double)(lo + hi);
+    upk2(fB, lo, hi); cols.acc[2][lane] += (double)(lo + hi);
+    upk2(fBg, lo, hi); cols.acc[3][lane] += (double)(lo + hi);
     fA = fAg = fB = fBg = kZero2;
   };
   // rows ping-pong between ra / rb so no register copies are needed; the taps of row i+2 are requested
@@ -150,11 +162,16 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     if ((i & 7) == 6) flush();
   }
   // i = 126: ra holds row 126, row 127 is in flight
-  upk2(ra[0], bot[0], bot[1]);
-  upk2(ra[1], bot[2], bot[3]);
+  {
+    float t0, t1, t2, t3;
+    upk2(ra[0], t0, t1);
+    upk2(ra[1], t2, t3);
+    *reinterpret_cast<float4*>(&cols.bot[4 * lane]) = make_float4(t0, t1, t2, t3);
+  }
   src.finish(rb);
   process(ra, rb, kCrop - 2);
   flush();
+  const double dA = cols.acc[0][lane], dAg = cols.acc[1][lane], dB = cols.acc[2][lane], dBg = cols.acc[3][lane];
   Deltas d;
   d.max_sdf = warp_max(mx);
   const float sumA = (float)warp_sum(dA);
@@ -175,12 +192,10 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
   float m_top = -INFINITY, m_bot = -INFINITY, m_left = -INFINITY, m_right = -INFINITY;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    if (c < 3 || lane < 31) {
-      m_top = fmaxf(m_top, movement(top[c]));
-      m_bot = fmaxf(m_bot, movement(bot[c]));
-    }
-    const int i = lane + 32 * c;
+    const int i = lane + 32 * c;   // position along the border; 127 is outside the region
     if (i < kCrop - 1) {
+      m_top = fmaxf(m_top, movement(cols.top[i]));
+      m_bot = fmaxf(m_bot, movement(cols.bot[i]));
       m_left = fmaxf(m_left, movement(cols.left[i]));
       m_right = fmaxf(m_right, movement(cols.right[i]));
     }
@@ -196,22 +211,11 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
 template <typename T>
 struct BoxT { T x1, y1, x2, y2; };
 
-// One round for one proposal, arithmetic in T (double on round 0 when the caller hands in
+// The box update of one round for one proposal, arithmetic in T (double on round 0 when the caller hands in
 // fp64 proposals — promotion at object_reasoning.py:190-194 — float afterwards).
 // Returns the label of this round and the updated box (fp32, :479).
 template <typename T>
-__device__ __forceinline__ int one_round(const RefineParams& p, const float* plane, BoxT<T> b, BorderCols& cols,
-                                         int lane, float4& out) {
-  out = make_float4(0.f, 0.f, 0.f, 0.f);
-  const Window win = snap_window<T>(b.x1, b.y1, b.x2, b.y2, p.W, p.H);
-  if (win.empty()) return -1;  // the reference would raise on a zero-size crop; defined as "no object"
-  CropRows src;
-  src.taps.init<kBlocked>(lane, win.w());
-  src.plane.init(plane, p.W, win);
-  src.in_h = win.h();
-  src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
-  const Deltas d = boundary_terms(src, cols, lane);
-  if (!(d.max_sdf > p.max_sdf_thres)) return -1;
+__device__ __forceinline__ int apply_update(const RefineParams& p, const Window& win, const Deltas& d, BoxT<T> b, float4& out) {
   // signed deltas: >0 expands, <0 shrinks; expansion is ignored on sides glued to the image edge (:444-447)
   float sg[4] = {-d.dx1, -d.dy1, d.dx2, d.dy2};
   const bool edge[4] = {win.x1 == 0, win.y1 == 0, win.x2 == p.W, win.y2 == p.H};
@@ -252,12 +256,12 @@ __device__ __forceinline__ int one_round(const RefineParams& p, const float* pla
 }
 
 #ifndef UNMORE_REFINE_WARPS
-#define UNMORE_REFINE_WARPS 8
+#define UNMORE_REFINE_WARPS 6
 #endif
 constexpr int kRefineWarps = UNMORE_REFINE_WARPS;
 
 #ifndef UNMORE_REFINE_MINBLOCKS
-#define UNMORE_REFINE_MINBLOCKS 2
+#define UNMORE_REFINE_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) refine_kernel(const RefineParams p) {
   __shared__ BorderCols cols_all[kRefineWarps];
@@ -271,30 +275,58 @@ __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) re
     worklist_locate(p.work, id, img, k);
     const size_t row = (size_t)img * p.work.cap + k;
     const float* plane = p.fields + ((size_t)img * p.C + p.ch_sdf) * p.H * p.W;
-    BoxT<double> bd;
-    load_box<double>(p.boxes, p.boxes_f64 != 0, row, bd.x1, bd.y1, bd.x2, bd.y2);
-    BoxT<float> bf = {(float)bd.x1, (float)bd.y1, (float)bd.x2, (float)bd.y2};
+    BoxT<float> bf;
+    {
+      double x1, y1, x2, y2;
+      load_box<double>(p.boxes, p.boxes_f64 != 0, row, x1, y1, x2, y2);
+      bf = {(float)x1, (float)y1, (float)x2, (float)y2};
+    }
     float4 cur = make_float4(bf.x1, bf.y1, bf.x2, bf.y2);
     float label = 0.f;
     int rounds = 0;
     for (int r = 0; r < p.n_round; ++r) {
+      // round 0 of fp64 proposals runs its window snap, area filter and box update in double; the fp64 box is
+      // re-read from memory where it is needed instead of living in registers through the resampling loop
       const bool dbl = (r == 0) && p.boxes_f64;
-      if (p.apply_small_filter) {  // filter_small_proposal (:293-299), strict '>'
-        bool keep;
-        if (dbl) keep = __dmul_rn(__dsub_rn(bd.x2, bd.x1), __dsub_rn(bd.y2, bd.y1)) > (double)p.area_thres;
-        else keep = __fmul_rn(__fsub_rn(bf.x2, bf.x1), __fsub_rn(bf.y2, bf.y1)) > p.area_thres;
-        if (!keep) { label = -2.f; break; }
+      Window win;
+      bool keep;
+      if (dbl) {
+        BoxT<double> bd;
+        load_box<double>(p.boxes, true, row, bd.x1, bd.y1, bd.x2, bd.y2);
+        keep = __dmul_rn(__dsub_rn(bd.x2, bd.x1), __dsub_rn(bd.y2, bd.y1)) > (double)p.area_thres;
+        win = snap_window<double>(bd.x1, bd.y1, bd.x2, bd.y2, p.W, p.H);
+      } else {
+        keep = __fmul_rn(__fsub_rn(bf.x2, bf.x1), __fsub_rn(bf.y2, bf.y1)) > p.area_thres;
+        win = snap_window<float>(bf.x1, bf.y1, bf.x2, bf.y2, p.W, p.H);
       }
-      float4 nb;
-      const int lab = dbl ? one_round<double>(p, plane, bd, cols, lane, nb) : one_round<float>(p, plane, bf, cols, lane, nb);
+      if (p.apply_small_filter && !keep) { label = -2.f; break; }  // filter_small_proposal (:293-299), strict '>'
+      float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+      int lab = -1;   // a zero-size crop (the reference would raise) is defined as "no object"
+      bool fixed = false;
+      if (!win.empty()) {
+        CropRows src;
+        src.taps.init<kBlocked>(lane, win.w());
+        src.plane.init(plane, p.W, win);
+        src.in_h = win.h();
+        src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
+        const Deltas d = boundary_terms(src, cols, lane);
+        if (d.max_sdf > p.max_sdf_thres) {
+          if (dbl) {
+            BoxT<double> bd;
+            load_box<double>(p.boxes, true, row, bd.x1, bd.y1, bd.x2, bd.y2);
+            lab = apply_update<double>(p, win, d, bd, nb);
+            // fp64 round 0: the fp32 cast must be exact and the fp32 area test of round 1 must agree
+            fixed = (double)nb.x == bd.x1 && (double)nb.y == bd.y1 && (double)nb.z == bd.x2 && (double)nb.w == bd.y2 &&
+                    (!p.apply_small_filter || __fmul_rn(__fsub_rn(nb.z, nb.x), __fsub_rn(nb.w, nb.y)) > p.area_thres);
+          } else {
+            lab = apply_update<float>(p, win, d, bf, nb);
+            fixed = true;
+          }
+        }
+      }
       rounds = r + 1;
       label = (float)lab;
-      // fp64 round 0: the fp32 cast must be exact and the fp32 area test of round 1 must agree
-      const bool fixed = lab == 1 && nb.x == cur.x && nb.y == cur.y && nb.z == cur.z && nb.w == cur.w &&
-                         (!dbl || ((double)nb.x == bd.x1 && (double)nb.y == bd.y1 && (double)nb.z == bd.x2 &&
-                                   (double)nb.w == bd.y2 &&
-                                   (!p.apply_small_filter ||
-                                    __fmul_rn(__fsub_rn(nb.z, nb.x), __fsub_rn(nb.w, nb.y)) > p.area_thres)));
+      fixed = fixed && lab == 1 && nb.x == cur.x && nb.y == cur.y && nb.z == cur.z && nb.w == cur.w;
       cur = nb;
       bf.x1 = nb.x; bf.y1 = nb.y; bf.x2 = nb.z; bf.y2 = nb.w;
       // label 1 with an unchanged box is an exact fixed point of the remaining rounds
