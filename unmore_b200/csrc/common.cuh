@@ -95,6 +95,9 @@ __device__ __forceinline__ f32x2 lerp_v2(f32x2 t0, f32x2 t1, float h0, float h1)
   return fma2(t0, pk2(h0, h0), mul2(t1, pk2(h1, h1)));
 }
 
+// a predicate that is the same in every lane, stated in a form the compiler can see (vote result)
+__device__ __forceinline__ bool warp_uniform(bool b) { return __any_sync(kFullMask, b) != 0; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

@@ -33,6 +33,13 @@ __device__ __forceinline__ float soft_fg(float s) {
   return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * s));
 }
 
+// one predicated store instead of a divergent branch around it (the compiler wraps `if (lane == k) smem = v`
+// in reconvergence bookkeeping: ~6 instructions per store in the row loop)
+__device__ __forceinline__ void st_shared_if(bool pred, float* smem_ptr, float v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.f32 [%1], %2; }" ::"r"((unsigned)pred), "r"(a), "f"(v) : "memory");
+}
+
 struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
   const float* tile;
   float4 pend;
@@ -89,15 +96,15 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
   for (int k = 0; k < 4; ++k) cols.acc[k][lane] = 0.0;
   const f32x2 kZero2 = pk2(0.f, 0.f), kOne2 = pk2(1.f, 1.f);
   f32x2 fA = kZero2, fAg = kZero2, fB = kZero2, fBg = kZero2;
-  const bool last_lane = lane == 31;
+  const bool first_lane = lane == 0, last_lane = lane == 31;
   // One output row of the 127x127 region: cur = S[i][.], nxt = S[i+1][.].
   auto process = [&](const f32x2 (&cur)[2], const f32x2 (&nxt)[2], int i) {
     float c0, c1, c2, c3, n0, n1, n2, n3;
     upk2(cur[0], c0, c1); upk2(cur[1], c2, c3);
     upk2(nxt[0], n0, n1); upk2(nxt[1], n2, n3);
     const float right = __shfl_down_sync(kFullMask, c0, 1);  // S[i][4l+4]
-    if (lane == 0) cols.left[i] = c0;     // column 0
-    if (last_lane) cols.right[i] = c2;    // column 126
+    st_shared_if(first_lane, &cols.left[i], c0);    // column 0
+    st_shared_if(last_lane, &cols.right[i], c2);    // column 126
     const f32x2 dx[2] = {pk2(c1 - c0, c2 - c1), pk2(c3 - c2, right - c3)};
     // the pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a); stage them so the
     // MUFU latencies overlap instead of serialising pixel after pixel

@@ -117,7 +117,8 @@ struct PlaneRows {
   // behind the work on row i.  The (cy0, cy1) bookkeeping depends only on tap indices, never on data, so
   // it can run ahead at issue time.
   struct Fetch {
-    int kind;   // 0 cache hit; 1 shift + new lower row (B); 2 both rows new (A, B); 3 one new row twice (A); 4 shift, clamped
+    bool load_a, load_b;   // row i0 / row i1 must be fetched (taps in a* / b*)
+    bool shift_a, dup_b;   // ra <- rb (the old lower row becomes the upper one); rb <- ra (clamped last row)
     float l0, l1;
     float a0[4], a1[4], b0[4], b1[4];
   };
@@ -129,43 +130,35 @@ struct PlaneRows {
       v1[c] = __ldg(byte_ptr(rowp, t.x1[c]));
     }
   }
+  // After the row: ra = H(i0), rb = H(i1).  H(i0) is the cached upper row, the cached lower row, or new;
+  // H(i1) is H(i0) again (clamped), the cached lower row, or new.  Every condition is a function of tap
+  // indices that are identical across the warp; routing them through a vote tells the compiler so and
+  // keeps the branches free of reconvergence bookkeeping.
   __device__ __forceinline__ void issue(const ColTaps& t, const AxisTap& v, Fetch& f) {
     f.l0 = v.l0; f.l1 = v.l1;
-    if (v.i0 == cy0 && v.i1 == cy1) { f.kind = 0; return; }   // all branches warp-uniform
-    if (v.i0 == cy1) {
-      if (v.i1 == v.i0) {
-        f.kind = 4;
-      } else {
-        f.kind = 1;
-        load_taps(t, v.i1, f.b0, f.b1);
-      }
-    } else {
-      load_taps(t, v.i0, f.a0, f.a1);
-      if (v.i1 == v.i0) {
-        f.kind = 3;
-      } else {
-        f.kind = 2;
-        load_taps(t, v.i1, f.b0, f.b1);
-      }
-    }
+    const bool keep_a = v.i0 == cy0;
+    f.shift_a = warp_uniform(!keep_a && v.i0 == cy1);
+    f.load_a = warp_uniform(!keep_a && v.i0 != cy1);
+    f.dup_b = warp_uniform(v.i1 == v.i0);
+    f.load_b = warp_uniform(v.i1 != v.i0 && v.i1 != cy1);
+    if (f.load_a) load_taps(t, v.i0, f.a0, f.a1);
+    if (f.load_b) load_taps(t, v.i1, f.b0, f.b1);
     cy0 = v.i0; cy1 = v.i1;
   }
   __device__ __forceinline__ void finish(const ColTaps& t, const Fetch& f, f32x2 out[2]) {
-    if (f.kind != 0) {
-      if (f.kind == 1 || f.kind == 4) {
-        ra[0] = rb[0]; ra[1] = rb[1];
-      } else {
+    if (f.load_a) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          ra[h] = lerp_h2(pk2(f.a0[2 * h], f.a0[2 * h + 1]), pk2(f.a1[2 * h], f.a1[2 * h + 1]), t.w0[h], t.w1[h]);
-      }
-      if (f.kind == 1 || f.kind == 2) {
+      for (int h = 0; h < 2; ++h)
+        ra[h] = lerp_h2(pk2(f.a0[2 * h], f.a0[2 * h + 1]), pk2(f.a1[2 * h], f.a1[2 * h + 1]), t.w0[h], t.w1[h]);
+    } else if (f.shift_a) {
+      ra[0] = rb[0]; ra[1] = rb[1];
+    }
+    if (f.load_b) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          rb[h] = lerp_h2(pk2(f.b0[2 * h], f.b0[2 * h + 1]), pk2(f.b1[2 * h], f.b1[2 * h + 1]), t.w0[h], t.w1[h]);
-      } else {
-        rb[0] = ra[0]; rb[1] = ra[1];
-      }
+      for (int h = 0; h < 2; ++h)
+        rb[h] = lerp_h2(pk2(f.b0[2 * h], f.b0[2 * h + 1]), pk2(f.b1[2 * h], f.b1[2 * h + 1]), t.w0[h], t.w1[h]);
+    } else if (f.dup_b) {
+      rb[0] = ra[0]; rb[1] = ra[1];
     }
     out[0] = lerp_v2(ra[0], rb[0], f.l0, f.l1);
     out[1] = lerp_v2(ra[1], rb[1], f.l0, f.l1);
