@@ -9,7 +9,7 @@
 // the packed rows and a 25-row AND.  Everything within 12 px of the crop border is eroded
 // away, which subsumes the reference's 10-px frame zeroing (:535-538), so only the central
 // 108x108 window of the center field (rows/cols 10..117) is ever read by the correlation:
-// that window is what is staged in shared memory (2 x 46,656 B -> two CTAs per SM).
+// that window is what is staged in shared memory (93,312 B, channels interleaved -> two CTAs per SM).
 #include "resample.cuh"
 #include "unmore_internal.h"
 
@@ -21,19 +21,19 @@ namespace unmore {
 constexpr int kCenterThreads = UNMORE_CENTER_THREADS;
 constexpr int kCenterWarps = kCenterThreads / 32;
 constexpr int kWinLo = 10, kWinHi = 118, kWin = kWinHi - kWinLo;  // staged window of the center field
+constexpr int kWinStride = 110;   // pixels per staged row: 880 B, so 8 lanes on consecutive rows hit 8 distinct 16-B bank groups
 constexpr int kErode = 12;                                         // 3 rounds x radius 4
 constexpr int kCcCap = UNMORE_CC_CAP;                               // component boxes kept per proposal
 
 struct CenterSmem {
-  float c0[kWin * kWin];
-  float c1[kWin * kWin];
+  float2 c[kWin * kWinStride];     // staged center field, (row, col) channels interleaved: one aligned pair per pixel
   uint32_t mask[kCrop][4];   // union mask, bit j of row i = column j (LSB = lowest column)
   uint32_t hrun[kCrop][4];   // horizontally eroded rows
   uint32_t ero[kCrop][4];    // fully eroded mask
   double red_val[kCenterWarps];
   int red_idx[kCenterWarps];
   float red_f[kCenterWarps];
-  float bcast_f[2];
+  float red_m[kCenterWarps];
   int bcast_i[2];
   int cc_scan[kCenterWarps];
   int cc_box[4][kCcCap];   // x_min, y_min, x_max, y_max per component (first kCcCap components)
@@ -173,8 +173,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
           const uint32_t word = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
           if (lane == 0) sm.mask[i][c] = word;
           if (i >= kWinLo && i < kWinHi && j >= kWinLo && j < kWinHi) {
-            sm.c0[(i - kWinLo) * kWin + (j - kWinLo)] = a[c];
-            sm.c1[(i - kWinLo) * kWin + (j - kWinLo)] = b[c];
+            sm.c[(i - kWinLo) * kWinStride + (j - kWinLo)] = make_float2(a[c], b[c]);
             cabs = fmaxf(cabs, fmaxf(fabsf(a[c]), fabsf(b[c])));
           }
         }
@@ -215,28 +214,37 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const uint32_t lo = sm.ero[r][c >> 5], hi = sm.ero[r][min((c >> 5) + 1, 3)];
         return (__funnelshift_r(lo, hi, c & 31)) & 0xffu;
       };
+      // acc[x] = sum over the 24 taps of f0*c0 + f1*c1 for the 8 pixels of the strip.  With the channels
+      // interleaved in shared memory every tap of every pixel is one aligned (c0, c1) pair, so a tap costs one
+      // FFMA2 against the (f0, f1) filter pair: the two channels accumulate in the two halves and are added
+      // at the end (the rounding differs from a single chain, which the screening margin covers).
       auto strip_scores = [&](int r, int k, float acc[8]) {
+        f32x2 acc2[8];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) acc[x] = 0.f;
+        for (int x = 0; x < 8; ++x) acc2[x] = pk2(0.f, 0.f);
         const int c = kErode + 8 * k;
 #pragma unroll
         for (int di = 0; di < 5; ++di) {
-          const int o = (r + di - 2 - kWinLo) * kWin + (c - 2 - kWinLo);  // multiple of 4 floats
-          float v0[12], v1[12];
+          const int o = (r + di - 2 - kWinLo) * kWinStride + (c - 2 - kWinLo);  // multiple of 4 pixels = 32 bytes
+          f32x2 v[12];
 #pragma unroll
-          for (int q4 = 0; q4 < 3; ++q4) {
-            const float4 t0 = *reinterpret_cast<const float4*>(&sm.c0[o + 4 * q4]);
-            const float4 t1 = *reinterpret_cast<const float4*>(&sm.c1[o + 4 * q4]);
-            v0[4 * q4] = t0.x; v0[4 * q4 + 1] = t0.y; v0[4 * q4 + 2] = t0.z; v0[4 * q4 + 3] = t0.w;
-            v1[4 * q4] = t1.x; v1[4 * q4 + 1] = t1.y; v1[4 * q4 + 2] = t1.z; v1[4 * q4 + 3] = t1.w;
+          for (int q2 = 0; q2 < 6; ++q2) {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(&sm.c[o + 2 * q2]);
+            v[2 * q2] = t.x; v[2 * q2 + 1] = t.y;
           }
 #pragma unroll
           for (int dj = 0; dj < 5; ++dj) {
             if (di == 2 && dj == 2) continue;
-            const float f0 = p.filt32[di * 5 + dj], f1 = p.filt32[dj * 5 + di];
+            const f32x2 f = pk2(p.filt32[di * 5 + dj], p.filt32[dj * 5 + di]);
 #pragma unroll
-            for (int x = 0; x < 8; ++x) acc[x] = fmaf(f0, v0[x + dj], fmaf(f1, v1[x + dj], acc[x]));
+            for (int x = 0; x < 8; ++x) acc2[x] = fma2(f, v[x + dj], acc2[x]);
           }
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          float lo, hi;
+          upk2(acc2[x], lo, hi);
+          acc[x] = lo + hi;
         }
       };
       float m32 = -INFINITY;
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         own_max[m] = -INFINITY;
         const int q = tid + m * kCenterThreads;
         if (q < kInner * kStrips) {
-          const int r = kErode + q / kStrips, k = q % kStrips;
+          const int r = kErode + q % kInner, k = q / kInner;   // consecutive lanes -> consecutive rows: conflict-free LDS.128
           const uint32_t bits = strip_bits(r, k);
           if (bits) {
             float acc[8];
@@ -259,16 +267,15 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       }
       m32 = warp_max(m32);
       float cmax = 0.f;
-      if (lane == 0) sm.red_val[warp] = (double)m32;
+      if (lane == 0) sm.red_m[warp] = m32;
       __syncthreads();
-      if (tid == 0) {
+      {  // every thread folds the per-warp partials itself (broadcast reads): no serial section, one barrier less
         float mm = -INFINITY, cm = 0.f;
-        for (int w = 0; w < kCenterWarps; ++w) { mm = fmaxf(mm, (float)sm.red_val[w]); cm = fmaxf(cm, sm.red_f[w]); }
-        sm.bcast_f[0] = mm; sm.bcast_f[1] = cm;
+#pragma unroll
+        for (int w = 0; w < kCenterWarps; ++w) { mm = fmaxf(mm, sm.red_m[w]); cm = fmaxf(cm, sm.red_f[w]); }
+        m32 = mm;
+        cmax = cm;
       }
-      __syncthreads();
-      m32 = sm.bcast_f[0];
-      cmax = sm.bcast_f[1];
       // |fp32 sum - exact sum| <= 48 ops * 2^-24 * sum|f||c| <= 48 * 2^-24 * 31 * cmax (before the / 24);
       // a tie of the true maximum can sit at most twice that below M32.  Padded x4.
       const float margin = 8.0f * 48.0f * 5.9604645e-08f * 31.0f * cmax;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       for (int m = 0; m < kMaxOwn; ++m) {
         if (!(own_max[m] >= m32 - margin) || m32 == -INFINITY) continue;
         const int q = tid + m * kCenterThreads;
-        const int r = kErode + q / kStrips, k = q % kStrips;
+        const int r = kErode + q % kInner, k = q / kInner;   // consecutive lanes -> consecutive rows: conflict-free LDS.128
         const uint32_t bits = strip_bits(r, k);
         float acc[8];
         strip_scores(r, k, acc);
@@ -292,9 +299,10 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
 #pragma unroll
             for (int dj = 0; dj < 5; ++dj) {
               if (di == 2 && dj == 2) continue;
-              const int o = (r + di - 2 - kWinLo) * kWin + (c + dj - 2 - kWinLo);
-              e = fma(p.filt[di * 5 + dj], (double)sm.c0[o], e);   // f[0][i][j] = (2-i)/n
-              e = fma(p.filt[dj * 5 + di], (double)sm.c1[o], e);   // f[1][i][j] = (2-j)/n
+              const int o = (r + di - 2 - kWinLo) * kWinStride + (c + dj - 2 - kWinLo);
+              const float2 cc = sm.c[o];
+              e = fma(p.filt[di * 5 + dj], (double)cc.x, e);   // f[0][i][j] = (2-i)/n
+              e = fma(p.filt[dj * 5 + di], (double)cc.y, e);   // f[1][i][j] = (2-j)/n
             }
           }
           e = __ddiv_rn(e, 24.0);
@@ -309,15 +317,18 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const int oi = __shfl_xor_sync(kFullMask, tidx, o);
         if (oi >= 0 && (tidx < 0 || ov > tbest || (ov == tbest && oi < tidx))) { tbest = ov; tidx = oi; }
       }
-      __syncthreads();  // red_val is reused
       if (lane == 0) { sm.red_val[warp] = tbest; sm.red_idx[warp] = tidx; }
       __syncthreads();
-      if (tid == 0) {
-        for (int w = 0; w < kCenterWarps; ++w) {
-          const double ov = sm.red_val[w];
-          const int oi = sm.red_idx[w];
-          if (oi >= 0 && (best_idx < 0 || ov > best || (ov == best && oi < best_idx))) { best = ov; best_idx = oi; }
+      if (warp == 0) {   // the first warp folds the per-warp results with shuffles
+        double ov = lane < kCenterWarps ? sm.red_val[lane] : 0.0;
+        int oi = lane < kCenterWarps ? sm.red_idx[lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double pv = __shfl_xor_sync(kFullMask, ov, o);
+          const int pi = __shfl_xor_sync(kFullMask, oi, o);
+          if (pi >= 0 && (oi < 0 || pv > ov || (pv == ov && pi < oi))) { ov = pv; oi = pi; }
         }
+        best = ov; best_idx = oi;
       }
     }
     if (tid == 0) {
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       __syncthreads();
       int n_comp = 0;
       if (sm.bcast_i[0] && !win.empty()) {
-        n_comp = label_components(sm.mask, reinterpret_cast<uint16_t*>(sm.c0), reinterpret_cast<uint16_t*>(sm.c1),
+        n_comp = label_components(sm.mask, reinterpret_cast<uint16_t*>(sm.c), reinterpret_cast<uint16_t*>(sm.c) + kCrop * kCrop,
                                   sm.cc_scan, sm.cc_box);   // the staged fields are dead now: reuse their storage
         if (n_comp >= 2) {
           if (tid < min(n_comp, kCcCap)) {
