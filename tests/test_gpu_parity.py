@@ -165,6 +165,34 @@ def test_scene_existence_and_center(golden_dir, od, dev, tag):
         assert np.array_equal(cr2["proposals_pass_singularity"].cpu().numpy(), g["pass2"])
 
 
+def test_center_reasoning_plateaus_and_ties(od, dev, ops):
+    """Center reasoning where the screening pass cannot separate the maximum: constant center fields (every
+    surviving pixel ties -> more exact-pass candidates than the queue holds) and a two-valued field whose seam
+    gives long runs of exactly equal maxima (argmax must be the first in raster order).  Against the oracle:
+    max values bit-equal, pass / split lists equal."""
+    H, W = 480, 640
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    props = torch.tensor(synth.make_proposals(5, 96, H, W))
+    args = O.make_args()
+    cases = []
+    f = torch.zeros((4, H, W)); f[0] = 1.0; f[1] = 0.6; f[2] = -0.3; f[3] = 1.0
+    cases.append(("constant", f))
+    f = torch.zeros((4, H, W)); f[0] = 1.0; f[3] = 1.0
+    f[1] = torch.where(yy < 240, 1.0, -1.0); f[2] = torch.where(xx < 320, 0.5, -0.5)   # vectors converge on the seams
+    cases.append(("seams", f))
+    f = torch.zeros((4, H, W)); f[0] = 1.0; f[3] = 1.0                                  # zero center field: all scores 0
+    cases.append(("zero", f))
+    for name, fields in cases:
+        ref = O.center_reasoning(fields, props, args, return_debug=True)
+        got = od.center_reasoning(fields.to(dev), props)
+        assert np.array_equal(got["proposals_pass_singularity"].cpu().numpy(), ref["proposals_pass_singularity"].numpy()), name
+        assert np.array_equal(got["splited_new_proposals"].cpu().numpy().reshape(-1, 4),
+                              ref["splited_new_proposals"].numpy().reshape(-1, 4)), name
+        mv, am, _, _ = ops.center_reasoning(fields.to(dev)[None].contiguous(), props.to(dev)[None].contiguous())[:4]
+        assert np.array_equal(mv[0].cpu().numpy(), ref["max_values"].numpy()), name
+    assert len(O.center_reasoning(cases[1][1], props, args)["splited_new_proposals"]) > 0   # the seam case does split
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_scene_single_rounds_teacher_forced(golden_dir, od, dev, tag):
     """optimize_one_image_single_round with inputs forced from the reference's own trajectory:

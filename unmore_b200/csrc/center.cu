@@ -23,6 +23,7 @@ constexpr int kCenterWarps = kCenterThreads / 32;
 constexpr int kWinLo = 10, kWinHi = 118, kWin = kWinHi - kWinLo;  // staged window of the center field
 constexpr int kWinStride = 110;   // pixels per staged row: 880 B, so 8 lanes on consecutive rows hit 8 distinct 16-B bank groups
 constexpr int kErode = 12;                                         // 3 rounds x radius 4
+constexpr int kCandCap = 1024;                                     // queue of pixels for the exact fp64 pass
 constexpr int kCcCap = UNMORE_CC_CAP;                               // component boxes kept per proposal
 
 struct CenterSmem {
@@ -36,6 +37,8 @@ struct CenterSmem {
   float red_m[kCenterWarps];
   int bcast_i[2];
   int cc_scan[kCenterWarps];
+  int cand_n;                // candidate pixels of the exact pass (b1 -> b2)
+  uint16_t cand[kCandCap];
   int cc_box[4][kCcCap];   // x_min, y_min, x_max, y_max per component (first kCcCap components)
 };
 
@@ -122,7 +125,10 @@ __device__ int label_components(const uint32_t (*mask)[4], uint16_t* lab, uint16
   return total;
 }
 
-template <bool ANALYZE_CC>
+// PLANE_ELEMS: 0 = any field size / channel order; H*W = the three channels are consecutive planes of a field
+// of exactly that size (the COCO-val shape the batch path runs on), see MultiPlaneRows.
+constexpr int kSpecPlaneElems = 480 * 640;
+template <bool ANALYZE_CC, int PLANE_ELEMS>
 __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CenterSmem& sm = *reinterpret_cast<CenterSmem*>(smem_raw);
@@ -150,13 +156,17 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       const float* base = p.fields + (size_t)img * p.C * plane_sz;
       const float* const planes[3] = {base + p.ch_sdf * plane_sz, base + p.ch_crow * plane_sz,
                                       base + p.ch_ccol * plane_sz};
-      MultiPlaneRows<3> rows;
+      MultiPlaneRows<3, PLANE_ELEMS> rows;
       rows.init(planes, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
-      float cabs = 0.f;  // max |center field| over the staged window: scales the fp32 screening margin
+      float cabs = 0.f;  // max |center field| over the tile (>= the staged window's): scales the fp32 screening margin
+      // staging predicates of this lane's four columns lane + 32c: columns 32..95 are always inside the window
+      const bool col_in[4] = {lane >= kWinLo, true, true, lane + 96 < kWinHi};
       for (int ii = 0; ii < kCrop / kCenterWarps; ++ii) {
         const int i = warp * (kCrop / kCenterWarps) + ii;
+        const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
+        float2* const stage = &sm.c[(i - kWinLo) * kWinStride + (lane - kWinLo)];
         const AxisTap v = axis_tap(scale_y, i, in_h);
         float sab[3][4];
         rows.row(taps, v, sab);
@@ -165,23 +175,21 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const float (&b)[4] = sab[2];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int j = lane + 32 * c;
           // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
           // equivalent threshold on the squared norm
           const float sq = __fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c]));
           const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
           const uint32_t word = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
           if (lane == 0) sm.mask[i][c] = word;
-          if (i >= kWinLo && i < kWinHi && j >= kWinLo && j < kWinHi) {
-            sm.c[(i - kWinLo) * kWinStride + (j - kWinLo)] = make_float2(a[c], b[c]);
-            cabs = fmaxf(cabs, fmaxf(fabsf(a[c]), fabsf(b[c])));
-          }
+          if (row_in && col_in[c]) stage[32 * c] = make_float2(a[c], b[c]);
+          cabs = fmaxf(cabs, fmaxf(fabsf(a[c]), fabsf(b[c])));
         }
       }
       cabs = warp_max(cabs);
       if (lane == 0) sm.red_f[warp] = cabs;
       __syncthreads();
       // ---- 2. erosion: 25-runs along rows, then AND of 25 rows
+      if (tid == kCrop) sm.cand_n = 0;   // an idle thread of this phase; ordered by the barriers around it
       if (tid < kCrop) {
         u128 m = load_row(sm.mask[tid]);
         m &= m >> 1; m &= m >> 2; m &= m >> 4; m &= m >> 8;  // bit j: columns j..j+15 set
@@ -279,35 +287,69 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       // |fp32 sum - exact sum| <= 48 ops * 2^-24 * sum|f||c| <= 48 * 2^-24 * 31 * cmax (before the / 24);
       // a tie of the true maximum can sit at most twice that below M32.  Padded x4.
       const float margin = 8.0f * 48.0f * 5.9604645e-08f * 31.0f * cmax;
-      double tbest = 0.0;
-      int tidx = -1;
+      // (b1) every pixel that can still be the maximum goes into a shared queue ...
+      const float cand_thr = m32 - margin;
+      const bool any_cand = m32 != -INFINITY;
 #pragma unroll
       for (int m = 0; m < kMaxOwn; ++m) {
-        if (!(own_max[m] >= m32 - margin) || m32 == -INFINITY) continue;
+        if (!any_cand || !(own_max[m] >= cand_thr)) continue;
         const int q = tid + m * kCenterThreads;
-        const int r = kErode + q % kInner, k = q / kInner;   // consecutive lanes -> consecutive rows: conflict-free LDS.128
+        const int r = kErode + q % kInner, k = q / kInner;
         const uint32_t bits = strip_bits(r, k);
         float acc[8];
         strip_scores(r, k, acc);
-#pragma unroll 1
+#pragma unroll
         for (int x = 0; x < 8; ++x) {
-          if (!((bits >> x) & 1u) || !(acc[x] >= m32 - margin)) continue;
-          const int c = kErode + 8 * k + x;
-          double e = 0.0;
-#pragma unroll
-          for (int di = 0; di < 5; ++di) {
-#pragma unroll
-            for (int dj = 0; dj < 5; ++dj) {
-              if (di == 2 && dj == 2) continue;
-              const int o = (r + di - 2 - kWinLo) * kWinStride + (c + dj - 2 - kWinLo);
-              const float2 cc = sm.c[o];
-              e = fma(p.filt[di * 5 + dj], (double)cc.x, e);   // f[0][i][j] = (2-i)/n
-              e = fma(p.filt[dj * 5 + di], (double)cc.y, e);   // f[1][i][j] = (2-j)/n
-            }
+          if (((bits >> x) & 1u) && acc[x] >= cand_thr) {
+            const int slot = atomicAdd(&sm.cand_n, 1);
+            if (slot < kCandCap) sm.cand[slot] = (uint16_t)(r * kCrop + kErode + 8 * k + x);
           }
-          e = __ddiv_rn(e, 24.0);
-          const int flat = r * kCrop + c;
+        }
+      }
+      __syncthreads();
+      // (b2) ... and is re-evaluated exactly as the reference does, one pixel per thread: the 96-term fp64
+      // chains of all candidates run side by side instead of one after the other in whichever thread owns them
+      auto exact = [&](int r, int c) -> double {
+        double e = 0.0;
+#pragma unroll
+        for (int di = 0; di < 5; ++di) {
+#pragma unroll
+          for (int dj = 0; dj < 5; ++dj) {
+            if (di == 2 && dj == 2) continue;
+            const float2 cc = sm.c[(r + di - 2 - kWinLo) * kWinStride + (c + dj - 2 - kWinLo)];
+            e = fma(p.filt[di * 5 + dj], (double)cc.x, e);   // f[0][i][j] = (2-i)/n
+            e = fma(p.filt[dj * 5 + di], (double)cc.y, e);   // f[1][i][j] = (2-j)/n
+          }
+        }
+        return __ddiv_rn(e, 24.0);
+      };
+      double tbest = 0.0;
+      int tidx = -1;
+      const int n_cand = sm.cand_n;
+      if (n_cand <= kCandCap) {
+        for (int q = tid; q < n_cand; q += kCenterThreads) {
+          const int flat = sm.cand[q];
+          const double e = exact(flat >> 7, flat & (kCrop - 1));
           if (tidx < 0 || e > tbest || (e == tbest && flat < tidx)) { tbest = e; tidx = flat; }
+        }
+      } else {
+        // a plateau (e.g. a constant field): more candidates than the queue holds; each thread walks its own strips
+#pragma unroll 1
+        for (int m = 0; m < kMaxOwn; ++m) {
+          if (!(own_max[m] >= cand_thr)) continue;
+          const int q = tid + m * kCenterThreads;
+          const int r = kErode + q % kInner, k = q / kInner;
+          const uint32_t bits = strip_bits(r, k);
+          float acc[8];
+          strip_scores(r, k, acc);
+#pragma unroll 1
+          for (int x = 0; x < 8; ++x) {
+            if (!((bits >> x) & 1u) || !(acc[x] >= cand_thr)) continue;
+            const int c = kErode + 8 * k + x;
+            const double e = exact(r, c);
+            const int flat = r * kCrop + c;
+            if (tidx < 0 || e > tbest || (e == tbest && flat < tidx)) { tbest = e; tidx = flat; }
+          }
         }
       }
       // block arg-max, ties -> smallest flat index (torch.argmax returns the first maximum)
@@ -507,15 +549,19 @@ int launch_components(const unsigned char* masks, int B, int* counts, int* boxes
   return (int)cudaGetLastError();
 }
 
-int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
+template <bool CC, int PE>
+static int launch_center_t(const CenterParams& p, int num_sms, cudaStream_t stream) {
   // function attributes are per device: set on every launch (microseconds), no cached state
-  cudaError_t e = p.cc_counts
-      ? cudaFuncSetAttribute(center_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem))
-      : cudaFuncSetAttribute(center_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+  cudaError_t e = cudaFuncSetAttribute(center_kernel<CC, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
   if (e != cudaSuccess) return (int)e;
-  if (p.cc_counts) center_kernel<true><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
-  else center_kernel<false><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
+  center_kernel<CC, PE><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
   return (int)cudaGetLastError();
+}
+
+int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
+  const bool spec = p.H * p.W == kSpecPlaneElems && p.ch_crow == p.ch_sdf + 1 && p.ch_ccol == p.ch_sdf + 2;
+  if (p.cc_counts) return spec ? launch_center_t<true, kSpecPlaneElems>(p, num_sms, stream) : launch_center_t<true, 0>(p, num_sms, stream);
+  return spec ? launch_center_t<false, kSpecPlaneElems>(p, num_sms, stream) : launch_center_t<false, 0>(p, num_sms, stream);
 }
 
 }  // namespace unmore

@@ -168,7 +168,10 @@ struct PlaneRows {
 // P channel planes of one window behind ONE row cache: the (cy0, cy1) bookkeeping and its branches
 // run once per output row instead of once per plane, and the taps of all planes of a source row
 // are requested together before any is consumed (P x 8 loads in flight).
-template <int P>
+// PLANE_ELEMS > 0: the P planes are consecutive channels of one image whose size is known at compile time;
+// the tap addresses are then formed once (plane 0) and the other planes are reached through the immediate
+// offset of the load instruction (P x 16 address instructions per source row become 16).
+template <int P, int PLANE_ELEMS = 0>
 struct MultiPlaneRows {
   const float* origin[P];
   int stride;
@@ -184,13 +187,27 @@ struct MultiPlaneRows {
   __device__ __forceinline__ void hrows(const ColTaps& t, int y, f32x2 out[P][2]) const {
     const int ro = y * stride;
     float v0[P][4], v1[P][4];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const float* rowp = elem_ptr(origin[p], ro);   // warp-uniform
+    if constexpr (PLANE_ELEMS > 0) {
+      const float* rowp = elem_ptr(origin[0], ro);   // warp-uniform
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        v0[p][c] = __ldg(byte_ptr(rowp, t.x0[c]));
-        v1[p][c] = __ldg(byte_ptr(rowp, t.x1[c]));
+        const float* a0 = byte_ptr(rowp, t.x0[c]);
+        const float* a1 = byte_ptr(rowp, t.x1[c]);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          v0[p][c] = __ldg(a0 + p * PLANE_ELEMS);
+          v1[p][c] = __ldg(a1 + p * PLANE_ELEMS);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const float* rowp = elem_ptr(origin[p], ro);   // warp-uniform
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          v0[p][c] = __ldg(byte_ptr(rowp, t.x0[c]));
+          v1[p][c] = __ldg(byte_ptr(rowp, t.x1[c]));
+        }
       }
     }
 #pragma unroll
