@@ -49,13 +49,14 @@ struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its
   __device__ __forceinline__ void finish(f32x2 out[2]) { out[0] = pk2(pend.x, pend.y); out[1] = pk2(pend.z, pend.w); }
 };
 
+template <int ROW_ELEMS>
 struct CropRows {  // crop window of the boundary-distance channel, resampled on the fly
   ColTaps taps;
   PlaneRows plane;
   PlaneRows::Fetch pend;
   float scale_y;
   int in_h;
-  __device__ __forceinline__ void issue(int /*lane*/, int i) { plane.issue(taps, axis_tap(scale_y, i, in_h), pend); }
+  __device__ __forceinline__ void issue(int /*lane*/, int i) { plane.issue<ROW_ELEMS>(taps, axis_tap(scale_y, i, in_h), pend); }
   __device__ __forceinline__ void finish(f32x2 out[2]) { plane.finish(taps, pend, out); }
 };
 
@@ -270,6 +271,8 @@ constexpr int kRefineWarps = UNMORE_REFINE_WARPS;
 #ifndef UNMORE_REFINE_MINBLOCKS
 #define UNMORE_REFINE_MINBLOCKS 3
 #endif
+constexpr int kSpecRowElems = 640;   // row pitch of the COCO-val-shaped fields the batch path runs on
+template <int ROW_ELEMS>
 __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) refine_kernel(const RefineParams p) {
   __shared__ BorderCols cols_all[kRefineWarps];
   const int lane = threadIdx.x & 31;
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) re
       int lab = -1;   // a zero-size crop (the reference would raise) is defined as "no object"
       bool fixed = false;
       if (!win.empty()) {
-        CropRows src;
+        CropRows<ROW_ELEMS> src;
         src.taps.init<kBlocked>(lane, win.w());
         src.plane.init(plane, p.W, win);
         src.in_h = win.h();
@@ -368,7 +371,8 @@ __global__ void __launch_bounds__(kRefineWarps * 32) tiles_kernel(const TilePara
 
 int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream) {
   const int ctas = num_sms * UNMORE_REFINE_MINBLOCKS;  // resident CTAs per SM; warps pull proposals dynamically
-  refine_kernel<<<ctas, kRefineWarps * 32, 0, stream>>>(p);
+  if (p.W == kSpecRowElems) refine_kernel<kSpecRowElems><<<ctas, kRefineWarps * 32, 0, stream>>>(p);
+  else refine_kernel<0><<<ctas, kRefineWarps * 32, 0, stream>>>(p);
   return (int)cudaGetLastError();
 }
 

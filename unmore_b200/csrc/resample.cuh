@@ -134,6 +134,10 @@ struct PlaneRows {
   // H(i1) is H(i0) again (clamped), the cached lower row, or new.  Every condition is a function of tap
   // indices that are identical across the warp; routing them through a vote tells the compiler so and
   // keeps the branches free of reconvergence bookkeeping.
+  // ROW_ELEMS > 0: the row pitch W is known at compile time; when both source rows of an output row are new
+  // (always the case when the crop is more than twice the tile height) they are adjacent, so the lower row's
+  // taps reuse the upper row's addresses through the load's immediate offset.
+  template <int ROW_ELEMS = 0>
   __device__ __forceinline__ void issue(const ColTaps& t, const AxisTap& v, Fetch& f) {
     f.l0 = v.l0; f.l1 = v.l1;
     const bool keep_a = v.i0 == cy0;
@@ -141,8 +145,24 @@ struct PlaneRows {
     f.load_a = warp_uniform(!keep_a && v.i0 != cy1);
     f.dup_b = warp_uniform(v.i1 == v.i0);
     f.load_b = warp_uniform(v.i1 != v.i0 && v.i1 != cy1);
-    if (f.load_a) load_taps(t, v.i0, f.a0, f.a1);
-    if (f.load_b) load_taps(t, v.i1, f.b0, f.b1);
+    if constexpr (ROW_ELEMS > 0) {
+      if (f.load_a && f.load_b) {        // i1 == i0 + 1
+        const float* rowp = elem_ptr(origin, v.i0 * ROW_ELEMS);   // warp-uniform
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float* p0 = byte_ptr(rowp, t.x0[c]);
+          const float* p1 = byte_ptr(rowp, t.x1[c]);
+          f.a0[c] = __ldg(p0); f.a1[c] = __ldg(p1);
+          f.b0[c] = __ldg(p0 + ROW_ELEMS); f.b1[c] = __ldg(p1 + ROW_ELEMS);
+        }
+      } else {
+        if (f.load_a) load_taps(t, v.i0, f.a0, f.a1);
+        if (f.load_b) load_taps(t, v.i1, f.b0, f.b1);
+      }
+    } else {
+      if (f.load_a) load_taps(t, v.i0, f.a0, f.a1);
+      if (f.load_b) load_taps(t, v.i1, f.b0, f.b1);
+    }
     cy0 = v.i0; cy1 = v.i1;
   }
   __device__ __forceinline__ void finish(const ColTaps& t, const Fetch& f, f32x2 out[2]) {
