@@ -126,7 +126,13 @@ int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W,
     return fail(UNMORE_E_INVALID, "unmore_center_reasoning: the three analyze_cc outputs go together");
   p.cc_counts = cc_counts_out; p.cc_boxes = cc_boxes_out; p.cc_overflow = cc_overflow;
   anti_center_filter(p.filt);
-  for (int i = 0; i < 25; ++i) p.filt32[i] = (float)p.filt[i];  // exact: the table is fp32-valued
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) {   // exact casts: the table is fp32-valued
+      const float f0 = (float)p.filt[i * 5 + j], f1 = (float)p.filt[j * 5 + i];
+      unsigned lo, hi;
+      memcpy(&lo, &f0, 4); memcpy(&hi, &f1, 4);
+      p.filt_pair[i * 5 + j] = ((unsigned long long)hi << 32) | lo;
+    }
   if (int e = make_worklist(p.work, counts, n_img, cap, ws, s)) return e;
   return cuda_fail(launch_center(p, num_sms(), s), "center_kernel");
 }

@@ -125,6 +125,86 @@ __device__ int label_components(const uint32_t (*mask)[4], uint16_t* lab, uint16
   return total;
 }
 
+// Row source of stage 1: the boundary-distance plane with the lane's columns paired (like PlaneRows) and the
+// two center-field planes paired PER COLUMN, (row, col) in one 64-bit register pair.  The packed lerps then
+// produce exactly the (c_row, c_col) pairs the staging store, the squared norm and the strip correlation
+// want, with no re-pairing moves.  Arithmetic per element is the same ATen bilinear as everywhere else.
+template <int PLANE_ELEMS>
+struct CenterRows {
+  const float* origin[3];
+  int stride;
+  int cy0, cy1;
+  f32x2 sa[2], sb[2];   // sdf: rows i0 / i1, element h = columns 2h, 2h+1 of the lane
+  f32x2 ca[4], cb[4];   // center field: rows i0 / i1, element c = (row, col) channels of column c
+
+  __device__ __forceinline__ void init(const float* const planes[3], int W, const Window& win) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) origin[p] = planes[p] + (size_t)win.y1 * W + win.x1;
+    stride = W;
+    cy0 = cy1 = -1;
+  }
+  __device__ __forceinline__ void hrows(const ColTaps& t, int y, f32x2 s[2], f32x2 cc[4]) const {
+    const int ro = y * stride;
+    float v0[3][4], v1[3][4];
+    if constexpr (PLANE_ELEMS > 0) {
+      const float* rowp = elem_ptr(origin[0], ro);   // warp-uniform
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* a0 = byte_ptr(rowp, t.x0[c]);
+        const float* a1 = byte_ptr(rowp, t.x1[c]);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          v0[p][c] = __ldg(a0 + p * PLANE_ELEMS);
+          v1[p][c] = __ldg(a1 + p * PLANE_ELEMS);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const float* rowp = elem_ptr(origin[p], ro);   // warp-uniform
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          v0[p][c] = __ldg(byte_ptr(rowp, t.x0[c]));
+          v1[p][c] = __ldg(byte_ptr(rowp, t.x1[c]));
+        }
+      }
+    }
+    float w0[4], w1[4];
+    upk2(t.w0[0], w0[0], w0[1]); upk2(t.w0[1], w0[2], w0[3]);
+    upk2(t.w1[0], w1[0], w1[1]); upk2(t.w1[1], w1[2], w1[3]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      s[h] = lerp_h2(pk2(v0[0][2 * h], v0[0][2 * h + 1]), pk2(v1[0][2 * h], v1[0][2 * h + 1]), t.w0[h], t.w1[h]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      cc[c] = lerp_h2(pk2(v0[1][c], v0[2][c]), pk2(v1[1][c], v1[2][c]), pk2(w0[c], w0[c]), pk2(w1[c], w1[c]));
+  }
+  // s[c] = sdf of column lane + 32c; ab[c] = (c_row, c_col) of that column
+  __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float s[4], f32x2 ab[4]) {
+    if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
+      if (v.i0 == cy1) {
+        sa[0] = sb[0]; sa[1] = sb[1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ca[c] = cb[c];
+      } else {
+        hrows(t, v.i0, sa, ca);
+      }
+      if (v.i1 == v.i0) {
+        sb[0] = sa[0]; sb[1] = sa[1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cb[c] = ca[c];
+      } else {
+        hrows(t, v.i1, sb, cb);
+      }
+      cy0 = v.i0; cy1 = v.i1;
+    }
+    upk2(lerp_v2(sa[0], sb[0], v.l0, v.l1), s[0], s[1]);
+    upk2(lerp_v2(sa[1], sb[1], v.l0, v.l1), s[2], s[3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ab[c] = lerp_v2(ca[c], cb[c], v.l0, v.l1);
+  }
+};
+
 // PLANE_ELEMS: 0 = any field size / channel order; H*W = the three channels are consecutive planes of a field
 // of exactly that size (the COCO-val shape the batch path runs on), see MultiPlaneRows.
 constexpr int kSpecPlaneElems = 480 * 640;
@@ -156,7 +236,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       const float* base = p.fields + (size_t)img * p.C * plane_sz;
       const float* const planes[3] = {base + p.ch_sdf * plane_sz, base + p.ch_crow * plane_sz,
                                       base + p.ch_ccol * plane_sz};
-      MultiPlaneRows<3, PLANE_ELEMS> rows;
+      CenterRows<PLANE_ELEMS> rows;
       rows.init(planes, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
@@ -168,21 +248,22 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
         float2* const stage = &sm.c[(i - kWinLo) * kWinStride + (lane - kWinLo)];
         const AxisTap v = axis_tap(scale_y, i, in_h);
-        float sab[3][4];
-        rows.row(taps, v, sab);
-        const float (&s)[4] = sab[0];
-        const float (&a)[4] = sab[1];
-        const float (&b)[4] = sab[2];
+        float s[4];
+        f32x2 ab[4];
+        rows.row(taps, v, s, ab);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
           // equivalent threshold on the squared norm
-          const float sq = __fadd_rn(__fmul_rn(a[c], a[c]), __fmul_rn(b[c], b[c]));
+          float a2, b2, a, b;
+          upk2(mul2(ab[c], ab[c]), a2, b2);
+          upk2(ab[c], a, b);
+          const float sq = __fadd_rn(a2, b2);
           const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
           const uint32_t word = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
           if (lane == 0) sm.mask[i][c] = word;
-          if (row_in && col_in[c]) stage[32 * c] = make_float2(a[c], b[c]);
-          cabs = fmaxf(cabs, fmaxf(fabsf(a[c]), fabsf(b[c])));
+          if (row_in && col_in[c]) *reinterpret_cast<f32x2*>(&stage[32 * c]) = ab[c];
+          cabs = fmaxf(cabs, fmaxf(fabsf(a), fabsf(b)));
         }
       }
       cabs = warp_max(cabs);
@@ -243,7 +324,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
 #pragma unroll
           for (int dj = 0; dj < 5; ++dj) {
             if (di == 2 && dj == 2) continue;
-            const f32x2 f = pk2(p.filt32[di * 5 + dj], p.filt32[dj * 5 + di]);
+            const f32x2 f = p.filt_pair[di * 5 + dj];
 #pragma unroll
             for (int x = 0; x < 8; ++x) acc2[x] = fma2(f, v[x + dj], acc2[x]);
           }

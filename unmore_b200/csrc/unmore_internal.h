@@ -66,7 +66,9 @@ struct CenterParams {
   // F.normalize(filter, dim=1) in fp32, then .double() (object_reasoning.py:372-373):
   // filt[i*5+j] = (2-i)/sqrt((2-i)^2+(2-j)^2); channel 1 uses the transposed entry
   double filt[25];
-  float filt32[25];    // the same values before the cast to double (fp32 screening pass)
+  // fp32 screening pass: (f[0][i][j], f[1][i][j]) as one aligned 64-bit pair per tap, so the packed FFMA2 reads
+  // its filter operand straight from the constant bank (no per-use pair assembly in uniform registers)
+  unsigned long long filt_pair[25];
   // --analyze_cc (object_reasoning.py:561-572); all three null when off
   unsigned char* cc_counts;  // [n_img, cap] component boxes emitted (0 unless the proposal passes with >= 2 components)
   double* cc_boxes;          // [n_img, cap, UNMORE_CC_CAP, 4] enlarged component boxes
