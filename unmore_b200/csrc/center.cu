@@ -242,15 +242,19 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       const int in_h = win.h();
       float cabs = 0.f;  // max |center field| over the tile (>= the staged window's): scales the fp32 screening margin
       // staging predicates of this lane's four columns lane + 32c: columns 32..95 are always inside the window
-      const bool col_in[4] = {lane >= kWinLo, true, true, lane + 96 < kWinHi};
-      for (int ii = 0; ii < kCrop / kCenterWarps; ++ii) {
+      const bool col_in[4] = {lane >= kWinLo, true, true, lane + 96 < kWinHi};   // [1], [2] unused: always inside
+      // shared addresses of this warp's first row: staging slot of column `lane`, mask words of the row
+      unsigned stage_addr = smem_addr(&sm.c[0]) + (unsigned)(((warp * (kCrop / kCenterWarps) - kWinLo) * kWinStride + (lane - kWinLo)) * 8);
+      unsigned mask_addr = smem_addr(&sm.mask[warp * (kCrop / kCenterWarps)][0]);
+      const bool lane0 = lane == 0;
+      for (int ii = 0; ii < kCrop / kCenterWarps; ++ii, stage_addr += kWinStride * 8, mask_addr += 16) {
         const int i = warp * (kCrop / kCenterWarps) + ii;
         const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
-        float2* const stage = &sm.c[(i - kWinLo) * kWinStride + (lane - kWinLo)];
         const AxisTap v = axis_tap(scale_y, i, in_h);
         float s[4];
         f32x2 ab[4];
         rows.row(taps, v, s, ab);
+        uint32_t word[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
@@ -260,11 +264,17 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
           upk2(ab[c], a, b);
           const float sq = __fadd_rn(a2, b2);
           const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
-          const uint32_t word = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
-          if (lane == 0) sm.mask[i][c] = word;
-          if (row_in && col_in[c]) *reinterpret_cast<f32x2*>(&stage[32 * c]) = ab[c];
+          word[c] = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
           cabs = fmaxf(cabs, fmaxf(fabsf(a), fabsf(b)));
         }
+        st_shared_b32_if<0>(lane0, mask_addr, word[0]);
+        st_shared_b32_if<4>(lane0, mask_addr, word[1]);
+        st_shared_b32_if<8>(lane0, mask_addr, word[2]);
+        st_shared_b32_if<12>(lane0, mask_addr, word[3]);
+        st_shared_b64_if<0>(row_in && col_in[0], stage_addr, ab[0]);
+        st_shared_b64_if<256>(row_in, stage_addr, ab[1]);
+        st_shared_b64_if<512>(row_in, stage_addr, ab[2]);
+        st_shared_b64_if<768>(row_in && col_in[3], stage_addr, ab[3]);
       }
       cabs = warp_max(cabs);
       if (lane == 0) sm.red_f[warp] = cabs;

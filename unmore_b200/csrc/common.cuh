@@ -95,6 +95,19 @@ __device__ __forceinline__ f32x2 lerp_v2(f32x2 t0, f32x2 t1, float h0, float h1)
   return fma2(t0, pk2(h0, h0), mul2(t1, pk2(h1, h1)));
 }
 
+// Predicated shared-memory stores on a 32-bit shared address with an immediate byte offset: one instruction
+// each.  (`if (pred) smem[i] = v` makes the compiler wrap the store in reconvergence bookkeeping and
+// re-derive the address per store: ~6 instructions in a row loop.)
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ void st_shared_b32_if(bool pred, unsigned addr, unsigned v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.b32 [%1+%3], %2; }" ::"r"((unsigned)pred), "r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void st_shared_b64_if(bool pred, unsigned addr, unsigned long long v) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.b64 [%1+%3], %2; }" ::"r"((unsigned)pred), "r"(addr), "l"(v), "n"(OFF) : "memory");
+}
+
 // a predicate that is the same in every lane, stated in a form the compiler can see (vote result)
 __device__ __forceinline__ bool warp_uniform(bool b) { return __any_sync(kFullMask, b) != 0; }
 

@@ -33,11 +33,9 @@ __device__ __forceinline__ float soft_fg(float s) {
   return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * s));
 }
 
-// one predicated store instead of a divergent branch around it (the compiler wraps `if (lane == k) smem = v`
-// in reconvergence bookkeeping: ~6 instructions per store in the row loop)
+// one predicated store instead of a divergent branch around it (common.cuh)
 __device__ __forceinline__ void st_shared_if(bool pred, float* smem_ptr, float v) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_ptr);
-  asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.f32 [%1], %2; }" ::"r"((unsigned)pred), "r"(a), "f"(v) : "memory");
+  st_shared_b32_if<0>(pred, smem_addr(smem_ptr), __float_as_uint(v));
 }
 
 struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
