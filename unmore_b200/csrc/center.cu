@@ -4,7 +4,7 @@
 // (utils/misc.py:10-20), evaluate the anti-center map (5x5 fp64 correlation, :360-377) on the
 // surviving pixels, and either pass the proposal (max <= thr) or split it at the arg-max.
 //
-// One CTA (512 threads) per proposal.  The mask lives as 128-bit rows; three 9x9 zero-border
+// One CTA (256 threads, two CTAs per SM) per proposal.  The mask lives as 128-bit rows; three 9x9 zero-border
 // erosions compose to a single 25x25 zero-border erosion, done with shift-AND doubling on
 // the packed rows and a 25-row AND.  Everything within 12 px of the crop border is eroded
 // away, which subsumes the reference's 10-px frame zeroing (:535-538), so only the central
@@ -16,7 +16,7 @@
 namespace unmore {
 
 #ifndef UNMORE_CENTER_THREADS
-#define UNMORE_CENTER_THREADS 512
+#define UNMORE_CENTER_THREADS 256
 #endif
 constexpr int kCenterThreads = UNMORE_CENTER_THREADS;
 constexpr int kCenterWarps = kCenterThreads / 32;
@@ -60,7 +60,7 @@ __device__ __forceinline__ void store_row(uint32_t r[4], u128 v) {
 __device__ int label_components(const uint32_t (*mask)[4], uint16_t* lab, uint16_t* rank, int* scan,
                                 int (*box)[kCcCap]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kPix = kCrop * kCrop, kPer = kPix / kCenterThreads;
+  constexpr int kPix = kCrop * kCrop, kPer = (kPix + kCenterThreads - 1) / kCenterThreads;
   auto bit = [&](int q) { return (mask[q >> 7][(q >> 5) & 3] >> (q & 31)) & 1u; };
   for (int q = tid; q < kPix; q += kCenterThreads) lab[q] = bit(q) ? (uint16_t)q : (uint16_t)0xFFFF;
   __syncthreads();
@@ -97,7 +97,7 @@ __device__ int label_components(const uint32_t (*mask)[4], uint16_t* lab, uint16
   }
   // rank the roots in raster order: thread t owns pixels [t*kPer, (t+1)*kPer)
   int mine = 0;
-  for (int q = tid * kPer; q < (tid + 1) * kPer; ++q) mine += (lab[q] == (uint16_t)q) ? 1 : 0;
+  for (int q = tid * kPer; q < min((tid + 1) * kPer, kPix); ++q) mine += (lab[q] == (uint16_t)q) ? 1 : 0;
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -110,7 +110,7 @@ __device__ int label_components(const uint32_t (*mask)[4], uint16_t* lab, uint16
   int base = 0, total = 0;
   for (int w = 0; w < kCenterWarps; ++w) { if (w < warp) base += scan[w]; total += scan[w]; }
   int rk = base + incl - mine;
-  for (int q = tid * kPer; q < (tid + 1) * kPer; ++q)
+  for (int q = tid * kPer; q < min((tid + 1) * kPer, kPix); ++q)
     if (lab[q] == (uint16_t)q) rank[q] = (uint16_t)min(rk++, 0xFFFF);
   __syncthreads();
   for (int q = tid; q < kPix; q += kCenterThreads) {
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
     double best = 0.0;
     int best_idx = -1;
     if (!win.empty()) {
-      // ---- 1. resample 3 channels; warp w owns output rows 8w .. 8w+7
+      // ---- 1. resample 3 channels; warp w owns kRowsPerWarp consecutive output rows
       ColTaps taps;
       taps.init<kStrided>(lane, win.w());
       const size_t plane_sz = (size_t)p.H * p.W;
@@ -244,11 +244,12 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       // staging predicates of this lane's four columns lane + 32c: columns 32..95 are always inside the window
       const bool col_in[4] = {lane >= kWinLo, true, true, lane + 96 < kWinHi};   // [1], [2] unused: always inside
       // shared addresses of this warp's first row: staging slot of column `lane`, mask words of the row
-      unsigned stage_addr = smem_addr(&sm.c[0]) + (unsigned)(((warp * (kCrop / kCenterWarps) - kWinLo) * kWinStride + (lane - kWinLo)) * 8);
-      unsigned mask_addr = smem_addr(&sm.mask[warp * (kCrop / kCenterWarps)][0]);
+      constexpr int kRowsPerWarp = (kCrop + kCenterWarps - 1) / kCenterWarps;
+      const int row_lo = warp * kRowsPerWarp, row_hi = min(kCrop, row_lo + kRowsPerWarp);
+      unsigned stage_addr = smem_addr(&sm.c[0]) + (unsigned)(((row_lo - kWinLo) * kWinStride + (lane - kWinLo)) * 8);
+      unsigned mask_addr = smem_addr(&sm.mask[0][0]) + 16u * (unsigned)row_lo;
       const bool lane0 = lane == 0;
-      for (int ii = 0; ii < kCrop / kCenterWarps; ++ii, stage_addr += kWinStride * 8, mask_addr += 16) {
-        const int i = warp * (kCrop / kCenterWarps) + ii;
+      for (int i = row_lo; i < row_hi; ++i, stage_addr += kWinStride * 8, mask_addr += 16) {
         const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
         const AxisTap v = axis_tap(scale_y, i, in_h);
         float s[4];
