@@ -268,10 +268,22 @@ def main():
             kernels[name] = {"ms_per_step": per_step[name], "share": per_step[name] / ms_per_step,
                              "ms_per_launch": stages[name]["ms"] / stages[name]["calls"], "achieved_gbs": ach,
                              "frac": ach / hbm_peak}
+    # ncu DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum of one --set full / --metrics
+    # capture of a launch of exactly this shape), committed under profiles/; None when the shape differs
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("images_per_launch") == chunk and tj.get("proposals_per_image") == n_prop and tj.get("field_hw") == [H, W]:
+            traffic = tj.get("dram_bytes_per_launch", {})
+    except Exception:
+        pass
+    for name, k in kernels.items():
+        k["traffic"] = traffic.get(name)
     dominant = max(per_step, key=per_step.get)
     dk = kernels.get(dominant, {"achieved_gbs": 0.0, "frac": 0.0})
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": dk["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": dk["frac"], "traffic": traffic.get(dominant), "peak_source": peak_src,
                 "note": "the per-proposal kernels re-read L2-resident fields and are bound by fp32/MUFU issue, not DRAM "
                         "(SURVEY.md §8d); only unmore_sat_build streams from HBM — see `kernels`",
                 "proposal_rounds_per_step": work["proposal_rounds"],
