@@ -215,12 +215,13 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
   __shared__ int s_id;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = worklist_total(p.work);
+  int img = 0;   // image of the previous work item: the locate hint
   for (;;) {
     if (tid == 0) s_id = atomicAdd(p.work.counter, 1);
     __syncthreads();
     const int id = s_id;
     if (id >= total) break;
-    int img, k;
+    int k;
     worklist_locate(p.work, id, img, k);
     const size_t row = (size_t)img * p.work.cap + k;
     double x1, y1, x2, y2;

@@ -157,11 +157,24 @@ __device__ __forceinline__ int worklist_next_warp(const WorkList& w) {
   return __shfl_sync(kFullMask, id, 0);
 }
 
+// `img` holds the image of the PREVIOUS item this warp / CTA pulled (0 before the first): ids only grow, so
+// the owner is found by walking forward from there — usually zero or one step — and the 8-probe binary
+// search (a chain of dependent loads with the CTA idle behind it) is only the fallback for long jumps.
 __device__ __forceinline__ void worklist_locate(const WorkList& w, int id, int& img, int& k) {
   if (!w.offsets) {
     img = id / w.cap;
     k = id - img * w.cap;
     return;
+  }
+  {
+    int cur = min(max(img, 0), w.n_img - 1);
+    int base = __ldg(w.offsets + cur);
+    if (base <= id) {
+      int steps = 0;
+      int next = __ldg(w.offsets + cur + 1);
+      while (next <= id && steps < 4) { ++cur; base = next; next = __ldg(w.offsets + cur + 1); ++steps; }
+      if (next > id) { img = cur; k = id - base; return; }
+    }
   }
   int lo = 0, hi = w.n_img;  // find img with offsets[img] <= id < offsets[img+1]
   while (hi - lo > 1) {

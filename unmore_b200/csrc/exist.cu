@@ -14,10 +14,11 @@ constexpr int kExistWarps = 8;
 __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const ExistParams p) {
   const int lane = threadIdx.x & 31;
   const int total = worklist_total(p.work);
+  int img = 0;   // image of the previous work item: the locate hint
   for (;;) {
     const int id = worklist_next_warp(p.work);
     if (id >= total) break;
-    int img, k;
+    int k;
     worklist_locate(p.work, id, img, k);
     const size_t row = (size_t)img * p.work.cap + k;
     double x1, y1, x2, y2;

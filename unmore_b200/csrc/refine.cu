@@ -276,10 +276,11 @@ __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) re
   const int lane = threadIdx.x & 31;
   BorderCols& cols = cols_all[threadIdx.x >> 5];
   const int total = worklist_total(p.work);
+  int img = 0;   // image of the previous work item: the locate hint
   for (;;) {
     const int id = worklist_next_warp(p.work);
     if (id >= total) break;
-    int img, k;
+    int k;
     worklist_locate(p.work, id, img, k);
     const size_t row = (size_t)img * p.work.cap + k;
     const float* plane = p.fields + ((size_t)img * p.C + p.ch_sdf) * p.H * p.W;
