@@ -212,20 +212,62 @@ template <bool ANALYZE_CC, int PLANE_ELEMS>
 __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CenterSmem& sm = *reinterpret_cast<CenterSmem*>(smem_raw);
-  __shared__ int s_id;
+  // Work items are fetched one proposal ahead by thread 0: the id is requested at the top of a proposal, the
+  // owner image is located after stage 1 (the atomic has long returned), the box is copied into shared memory
+  // by cp.async (no registers, nothing waits on it) and everything is published by the barrier that ends the
+  // proposal — so a new proposal starts from shared memory instead of a chain of dependent global accesses.
+  struct WorkItem { int id, img, k, pad; double box[4]; };
+  __shared__ __align__(16) WorkItem s_item[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int total = worklist_total(p.work);
-  int img = 0;   // image of the previous work item: the locate hint
-  for (;;) {
-    if (tid == 0) s_id = atomicAdd(p.work.counter, 1);
-    __syncthreads();
-    const int id = s_id;
+  auto fetch_box = [&](int slot, int fimg, int fk) {   // thread 0 only
+    const size_t frow = (size_t)fimg * p.work.cap + fk;
+    const unsigned dst = smem_addr(&s_item[slot].box[0]);
+    if (p.boxes_f64) {
+      const char* src = reinterpret_cast<const char*>(p.boxes) + frow * 32;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+    } else {
+      const char* src = reinterpret_cast<const char*>(p.boxes) + frow * 16;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+  };
+  if (tid == 0) {
+    const int id0 = atomicAdd(p.work.counter, 1);
+    int img0 = 0, k0 = 0;
+    if (id0 < total) {
+      worklist_locate(p.work, id0, img0, k0);
+      fetch_box(0, img0, k0);
+    }
+    s_item[0].id = id0; s_item[0].img = img0; s_item[0].k = k0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const int cur = it & 1;
+    const int id = s_item[cur].id;
     if (id >= total) break;
-    int k;
-    worklist_locate(p.work, id, img, k);
+    const int img = s_item[cur].img, k = s_item[cur].k;
     const size_t row = (size_t)img * p.work.cap + k;
     double x1, y1, x2, y2;
-    load_box<double>(p.boxes, p.boxes_f64 != 0, row, x1, y1, x2, y2);
+    if (p.boxes_f64) {
+      x1 = s_item[cur].box[0]; y1 = s_item[cur].box[1]; x2 = s_item[cur].box[2]; y2 = s_item[cur].box[3];
+    } else {
+      const float* bf = reinterpret_cast<const float*>(&s_item[cur].box[0]);
+      x1 = bf[0]; y1 = bf[1]; x2 = bf[2]; y2 = bf[3];
+    }
+    int next_id = total, next_img = img, next_k = 0;
+    if (tid == 0) next_id = atomicAdd(p.work.counter, 1);
+    bool next_located = false;
+    auto locate_next = [&]() {   // thread 0, once per proposal, well after the atomic was issued
+      if (tid == 0 && !next_located) {
+        if (next_id < total) {
+          worklist_locate(p.work, next_id, next_img, next_k);
+          fetch_box(cur ^ 1, next_img, next_k);
+        }
+        next_located = true;
+      }
+    };
     const Window win = snap_window<double>(x1, y1, x2, y2, p.W, p.H);
     double best = 0.0;
     int best_idx = -1;
@@ -281,6 +323,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       cabs = warp_max(cabs);
       if (lane == 0) sm.red_f[warp] = cabs;
       __syncthreads();
+      locate_next();
       // ---- 2. erosion: 25-runs along rows, then AND of 25 rows
       if (tid == kCrop) sm.cand_n = 0;   // an idle thread of this phase; ordered by the barriers around it
       if (tid < kCrop) {
@@ -515,7 +558,12 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       }
       if (tid == 0) p.cc_counts[row] = (unsigned char)(n_comp >= 2 ? min(n_comp, kCcCap) : 0);
     }
-    __syncthreads();  // s_id and shared tiles are reused by the next proposal
+    locate_next();   // zero-size crops skip the stages above
+    if (tid == 0) {
+      s_item[cur ^ 1].id = next_id; s_item[cur ^ 1].img = next_img; s_item[cur ^ 1].k = next_k;
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();  // publishes the next work item; shared tiles are reused by the next proposal
   }
 }
 
