@@ -38,13 +38,14 @@ __device__ __forceinline__ void st_shared_if(bool pred, float* smem_ptr, float v
   st_shared_b32_if<0>(pred, smem_addr(smem_ptr), __float_as_uint(v));
 }
 
-struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its float4
+struct TileRows {  // pre-resampled [128,128] tile (unit op a10): lane reads its four columns lane + 32c
   const float* tile;
-  float4 pend;
+  float pend[4];
   __device__ __forceinline__ void issue(int lane, int i) {
-    pend = __ldg(reinterpret_cast<const float4*>(tile + i * kCrop) + lane);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pend[c] = __ldg(tile + i * kCrop + lane + 32 * c);
   }
-  __device__ __forceinline__ void finish(f32x2 out[2]) { out[0] = pk2(pend.x, pend.y); out[1] = pk2(pend.z, pend.w); }
+  __device__ __forceinline__ void finish(f32x2 out[2]) { out[0] = pk2(pend[0], pend[1]); out[1] = pk2(pend[2], pend[3]); }
 };
 
 template <int ROW_ELEMS>
@@ -74,7 +75,7 @@ struct Deltas {
   float dx1, dy1, dx2, dy2;
 };
 
-// a10 on one proposal.  `src.issue(lane, i)` / `src.finish(out)` yield S[i][4*lane .. 4*lane+3] as two packed pairs.
+// a10 on one proposal.  `src.issue(lane, i)` / `src.finish(out)` yield S[i][lane + 32c], c = 0..3, as two packed pairs.
 // The per-pixel formula runs on pairs (FFMA2 / FMUL2 / FADD2): one issue slot per two pixels for
 // everything but the three MUFU evaluations and the horizontal difference.
 template <class RowSrc>
@@ -89,22 +90,30 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     upk2(ra[0], t0, t1);
     upk2(ra[1], t2, t3);
     mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-    *reinterpret_cast<float4*>(&cols.top[4 * lane]) = make_float4(t0, t1, t2, t3);
+    cols.top[lane] = t0; cols.top[lane + 32] = t1; cols.top[lane + 64] = t2; cols.top[lane + 96] = t3;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) cols.acc[k][lane] = 0.0;
   const f32x2 kZero2 = pk2(0.f, 0.f), kOne2 = pk2(1.f, 1.f);
   f32x2 fA = kZero2, fAg = kZero2, fB = kZero2, fBg = kZero2;
   const bool first_lane = lane == 0, last_lane = lane == 31;
+  const int next_lane = (lane + 1) & 31;
   // One output row of the 127x127 region: cur = S[i][.], nxt = S[i+1][.].
   auto process = [&](const f32x2 (&cur)[2], const f32x2 (&nxt)[2], int i) {
     float c0, c1, c2, c3, n0, n1, n2, n3;
     upk2(cur[0], c0, c1); upk2(cur[1], c2, c3);
     upk2(nxt[0], n0, n1); upk2(nxt[1], n2, n3);
-    const float right = __shfl_down_sync(kFullMask, c0, 1);  // S[i][4l+4]
-    st_shared_if(first_lane, &cols.left[i], c0);    // column 0
-    st_shared_if(last_lane, &cols.right[i], c2);    // column 126
-    const f32x2 dx[2] = {pk2(c1 - c0, c2 - c1), pk2(c3 - c2, right - c3)};
+    // Lane l holds columns l, l+32, l+64, l+96 (a tap request of the warp then covers 32 consecutive output
+    // columns, ~5 L1 sectors instead of ~26 with four adjacent columns per lane — the L1 data pipe was the
+    // busiest unit of this kernel).  The right neighbour of column l+32c is the next lane's same element, or
+    // lane 0's NEXT element for lane 31; lane 0 therefore hands out its elements shifted by one.
+    const float r0 = __shfl_sync(kFullMask, first_lane ? c1 : c0, next_lane);
+    const float r1 = __shfl_sync(kFullMask, first_lane ? c2 : c1, next_lane);
+    const float r2 = __shfl_sync(kFullMask, first_lane ? c3 : c2, next_lane);
+    const float r3 = __shfl_sync(kFullMask, c3, next_lane);   // lane 31: column 128 does not exist (pixel excluded below)
+    st_shared_if(first_lane, &cols.left[i], c0);        // column 0
+    st_shared_if(lane == 30, &cols.right[i], c3);       // column 126 = 30 + 96
+    const f32x2 dx[2] = {pk2(r0 - c0, r1 - c1), pk2(r2 - c2, r3 - c3)};
     // the pixels of a lane are independent dependency chains (ex2 -> +1 -> rcp -> 1-a); stage them so the
     // MUFU latencies overlap instead of serialising pixel after pixel
     f32x2 t[2], u[2], g[2], a[2];
@@ -135,7 +144,7 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
       fB = add2(fB, b);    fBg = fma2(b, g[0], fBg);
     }
     {
-      // column 127 (second pixel of the upper pair of lane 31) is outside the 127x127 region: its
+      // column 127 (lane 31's fourth column = second pixel of its upper pair) is outside the 127x127 region: its
       // foreground and background weights are forced to zero
       float al, ah, bl, bh;
       upk2(a[1], al, ah);
@@ -172,7 +181,7 @@ __device__ __forceinline__ Deltas boundary_terms(RowSrc& src, BorderCols& cols, 
     float t0, t1, t2, t3;
     upk2(ra[0], t0, t1);
     upk2(ra[1], t2, t3);
-    *reinterpret_cast<float4*>(&cols.bot[4 * lane]) = make_float4(t0, t1, t2, t3);
+    cols.bot[lane] = t0; cols.bot[lane + 32] = t1; cols.bot[lane + 64] = t2; cols.bot[lane + 96] = t3;
   }
   src.finish(rb);
   process(ra, rb, kCrop - 2);
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) re
       bool fixed = false;
       if (!win.empty()) {
         CropRows<ROW_ELEMS> src;
-        src.taps.init<kBlocked>(lane, win.w());
+        src.taps.init<kStrided>(lane, win.w());
         src.plane.init(plane, p.W, win);
         src.in_h = win.h();
         src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
