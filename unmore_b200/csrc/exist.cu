@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const Exist
     float score = 0.f;  // zero-size crop: the reference raises; defined as "nothing there"
     if (!win.empty()) {
       ColTaps taps;
-      taps.init<kBlocked>(lane, win.w());
+      taps.init<kStrided>(lane, win.w());
       PlaneRows plane;
       plane.init(p.fields + ((size_t)img * p.C + p.ch_exist) * p.H * p.W, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);

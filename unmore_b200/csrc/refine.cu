@@ -53,13 +53,35 @@ struct CropRows {  // crop window of the boundary-distance channel, resampled on
   ColTaps taps;
   PlaneRows plane;
   PlaneRows::Fetch pend;
-  float scale_y;
+  unsigned tapy_addr;   // shared address of this warp's vertical-tap table (BorderCols::tapy)
   int in_h;
-  __device__ __forceinline__ void issue(int /*lane*/, int i) { plane.issue<ROW_ELEMS>(taps, axis_tap(scale_y, i, in_h), pend); }
+  // The 128 vertical taps of the window are computed once per round, four per lane, and read back as one
+  // broadcast 8-byte load per row (instead of ten instructions of tap arithmetic per row).
+  __device__ __forceinline__ void init_rows(int lane, int2* tapy, int h) {
+    in_h = h;
+    const float scale_y = __fdiv_rn((float)h, (float)kCrop);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const AxisTap t = axis_tap(scale_y, lane + 32 * k, h);
+      tapy[lane + 32 * k] = make_int2(t.i0, __float_as_int(t.l1));
+    }
+    tapy_addr = smem_addr(tapy);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void issue(int /*lane*/, int i) {
+    int i0, l1b;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(i0), "=r"(l1b) : "r"(tapy_addr + 8u * (unsigned)i) : "memory");
+    AxisTap v;
+    v.i0 = i0;
+    v.i1 = min(i0 + 1, in_h - 1);
+    v.l1 = __int_as_float(l1b);
+    v.l0 = __fsub_rn(1.f, v.l1);
+    plane.issue<ROW_ELEMS>(taps, v, pend);
+  }
   __device__ __forceinline__ void finish(f32x2 out[2]) { plane.finish(taps, pend, out); }
 };
 
-// Per-warp scratch (3 KB): the four borders of the resampled tile — S[i][0], S[i][126] for i in [0,127),
+// Per-warp scratch (4 KB): the four borders of the resampled tile — S[i][0], S[i][126] for i in [0,127),
 // S[0][j], S[126][j] — so the border pass needs no resample, and the fp64 running sums of each lane.
 // Keeping these out of registers is what lets the split-phase row fetch fit the register budget.
 struct BorderCols {
@@ -68,6 +90,7 @@ struct BorderCols {
   float top[kCrop];
   float bot[kCrop];
   double acc[4][32];   // sum A, sum A*g, sum B, sum B*g per lane
+  int2 tapy[kCrop];    // vertical taps of the current window: (i0, bits of l1) per output row
 };
 
 struct Deltas {
@@ -325,8 +348,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32, UNMORE_REFINE_MINBLOCKS) re
         CropRows<ROW_ELEMS> src;
         src.taps.init<kStrided>(lane, win.w());
         src.plane.init(plane, p.W, win);
-        src.in_h = win.h();
-        src.scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
+        src.init_rows(lane, cols.tapy, win.h());
         const Deltas d = boundary_terms(src, cols, lane);
         if (d.max_sdf > p.max_sdf_thres) {
           if (dbl) {
