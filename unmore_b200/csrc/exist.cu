@@ -12,7 +12,10 @@ namespace unmore {
 constexpr int kExistWarps = 8;
 
 __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const ExistParams p) {
+  __shared__ int2 tapy_all[kExistWarps][kCrop];   // vertical taps of the warp's current window: (i0, bits of l1)
   const int lane = threadIdx.x & 31;
+  int2* const tapy = tapy_all[threadIdx.x >> 5];
+  const unsigned tapy_addr = smem_addr(tapy);
   const int total = worklist_total(p.work);
   int img = 0;   // image of the previous work item: the locate hint
   for (;;) {
@@ -32,11 +35,24 @@ __global__ void __launch_bounds__(kExistWarps * 32) existence_kernel(const Exist
       plane.init(p.fields + ((size_t)img * p.C + p.ch_exist) * p.H * p.W, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
+      // the 128 vertical taps once per proposal, four per lane; one broadcast 8-byte load per row afterwards
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const AxisTap t = axis_tap(scale_y, lane + 32 * q, in_h);
+        tapy[lane + 32 * q] = make_int2(t.i0, __float_as_int(t.l1));
+      }
+      __syncwarp();
       double acc = 0.0;
       f32x2 part = pk2(0.f, 0.f);   // two fp32 partial sums per lane, flushed to fp64 every 8 rows
       for (int i = 0; i < kCrop; ++i) {
         f32x2 v[2];
-        plane.row2(taps, axis_tap(scale_y, i, in_h), v);
+        int i0, l1b;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(i0), "=r"(l1b) : "r"(tapy_addr + 8u * (unsigned)i) : "memory");
+        AxisTap vt;
+        vt.i0 = i0; vt.i1 = min(i0 + 1, in_h - 1);
+        vt.l1 = __int_as_float(l1b); vt.l0 = __fsub_rn(1.f, vt.l1);
+        plane.row2(taps, vt, v);
         part = add2(part, add2(v[0], v[1]));
         if ((i & 7) == 7) {
           float lo, hi;
