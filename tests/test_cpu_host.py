@@ -151,3 +151,28 @@ def test_gather_detections_world2_gloo(tmp_path):
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/unmore_b200.h is the drop-in boundary: it must compile as C (no C++ or torch types in the
+    signatures) and a C program must link against the library and call its non-compute entry points."""
+    import shutil
+    import subprocess
+    from unmore_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "unmore_b200.h"\n'
+                   'int main(void) { printf("%d %d %zu\\n", unmore_version(), unmore_cc_cap(), (size_t)unmore_workspace_bytes(3));\n'
+                   '  const char* e = unmore_last_error(); return e == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                    "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) >= 100 and int(out[1]) >= 1 and int(out[2]) > 0
+    # and as C++ (extern "C" guards)
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "unmore_b200.h"\nint main() { return unmore_version() < 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-c", str(cpp), "-o", str(tmp_path / "t.o")], check=True)
