@@ -316,6 +316,30 @@ def test_discovery_and_scoring_vs_oracle(dev, od, seed):
         assert np.array_equal(masks, s_ref["masks"])
 
 
+@pytest.mark.parametrize("hw", [(640, 480), (320, 640), (960, 320), (200, 360)])
+def test_kernel_specialisations_on_other_shapes(dev, hw):
+    """The hot kernels have compile-time specialisations keyed on the field geometry (center: plane size
+    480*640 with consecutive channels; refine: row pitch 640).  Shapes that hit one specialisation but not the
+    other — 640x480 (same plane size, other pitch), 320x640 and 960x320 (same pitch or same area with another
+    layout) — and one that hits neither must all agree with the oracle."""
+    from unmore_b200.object_reasoning import Object_Discovery
+    from unmore_b200.object_scoring import Object_Scoring
+    H, W = hw
+    args = O.make_args()
+    img = synth.make_fields(77, H, W)
+    props = synth.make_proposals(77, 128, H, W)
+    ref = O.discover_image(img, props, args)
+    od = Object_Discovery(device=dev)
+    od.height, od.width = H, W
+    det = od.discover_image(img.to(dev), props)
+    assert_boxes_close(det, ref, f"discovered vs oracle at {H}x{W}")
+    if len(ref):
+        s_ref = O.score_image(img, ref.tolist(), args)
+        anns = Object_Scoring(device=dev).score_image(img.to(dev), ref.astype(np.float64).tolist())
+        assert_rel([a["score"] for a in anns], s_ref["score"], "score")
+        assert np.array_equal(np.stack([a["segmentation"]["mask"] for a in anns]), s_ref["masks"])
+
+
 def test_rasterise_both_resize_paths_vs_oracle(dev):
     """Boxes chosen so that h+w <= 128 (ATen's small-output kernel) and > 128 (generic kernel),
     dyadic sizes with exact 0.5 ties, image-edge boxes, one-pixel boxes."""
