@@ -1,7 +1,7 @@
 """Seeded fuzz: full discovery + scoring on the GPU against the CPU oracle, many scenes.
 Reports every mismatch with its size so forks can be attributed."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import oracle as O
 from unmore_b200 import synth

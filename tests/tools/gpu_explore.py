@@ -1,13 +1,13 @@
 """Exploratory GPU-vs-oracle error report (not a test)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import oracle as O
 from unmore_b200 import synth, ops
 from unmore_b200.object_reasoning import Object_Discovery
 
 dev = torch.device("cuda:0")
-G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+G = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden")
 od = Object_Discovery(device=dev)
 args = O.make_args()
 
