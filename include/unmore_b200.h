@@ -168,11 +168,23 @@ int unmore_mask_resize(const unsigned char* masks, int B, int H, int W, int out_
  * (post_process.py:61-74) for the detections kept by the second NMS, in keep order:
  * out [n_img, cap, 5] fp64 = (score, existence_score, center_score, boundary_score, area_score);
  * bbox_xywh_out [n_img, cap, 4] fp32 COCO box; selected_out (nullable) [n_img, cap] u8 = 1 unless
- * existence < t_e or center < t_c or boundary < t_b. */
+ * existence < t_e or center < t_c or boundary < t_b — the thresholds are doubles and the fp32 scores are
+ * compared in double, like the reference's Python floats (post_process.py:64-69), so a threshold that
+ * is not representable in fp32 (0.7, ...) selects the same set. */
 int unmore_final_scores(const float* scores, const float* tight, const int* areas, const int* keep,
-                        const int* keep_counts, int cap, int n_img, float existence_score_thres,
-                        float center_score_thres, float boundary_score_thres, double* out,
+                        const int* keep_counts, int cap, int n_img, double existence_score_thres,
+                        double center_score_thres, double boundary_score_thres, double* out,
                         float* bbox_xywh_out, unsigned char* selected_out, unmore_stream_t stream);
+
+/* Detection rows for the end-of-run collective (the image-sharded driver that formalises the reference's
+ * --start_idx / --end_idx processes, datasets.py:432-435 + object_reasoning.py:662-665): appends the
+ * detections of a batch to a fixed-capacity row buffer `rows` [max_rows + 1, 6] fp64 in image-major, NMS
+ * keep order.  rows[0] = (row count so far, overflow flag, 0, 0, 0, 0) is the header and the append cursor
+ * (zero it before the first batch); rows[1 + r] = (image_id, x, y, w, h, score).  image_ids [n_img] int64;
+ * bbox_xywh [n_img, cap, 4] fp32 and out5 [n_img, cap, 5] fp64 as written by unmore_final_scores. */
+int unmore_pack_detections(const long long* image_ids, const float* bbox_xywh, const double* out5,
+                           const int* keep_counts, int cap, int n_img, double* rows, int max_rows,
+                           unmore_stream_t stream);
 
 /* Summed-area tables (north-star op (a); no reference counterpart, oracle = fp64 cumsum):
  * in [n_planes, H, W] fp32 -> out [n_planes, H+1, W+1] fp64, out[y][x] = sum in[:y, :x]. W <= 2048. */

@@ -481,7 +481,7 @@ def discover_image(image: torch.Tensor, proposals, args, debug: Optional[dict] =
         return empty
     final = br["proposals"][br["labels"] == 1]
     if debug is not None:
-        debug["refine_out"], debug["refine_labels"] = br["proposals"], br["labels"]
+        debug["refine_out"], debug["refine_labels"], debug["refine_index"] = br["proposals"], br["labels"], br["index"]
     if len(final) == 0:
         return empty
     keep = nms(final.numpy(), np.ones(len(final), dtype=np.float32), args.nms_iou)

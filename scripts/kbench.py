@@ -31,11 +31,23 @@ ws = ops.workspace(n_img, dev)
 if which & {"all", "exist"}:
     mn, av = timeit(lambda: ops.existence_scores(fields, props, None, ws=ws))
     print(f"exist   : {mn:8.3f} ms min {av:8.3f} avg  {n_img*N/mn/1e3:8.2f} Mprop/s")
+    ex = ops.existence_scores(fields, props, None, ws=ws).cpu()
+    if os.environ.get("KB_SAVE"):
+        torch.save(ex, os.environ["KB_SAVE"] + ".exist")
+    if os.environ.get("KB_CMP") and os.path.exists(os.environ["KB_CMP"] + ".exist"):
+        print("   vs saved: existence scores bit-equal", bool(torch.equal(torch.load(os.environ["KB_CMP"] + ".exist"), ex)))
 if which & {"all", "center"}:
     p1, c1 = st["pass1_boxes"], st["pass1"]
     n = int(c1.sum())
     mn, av = timeit(lambda: ops.center_reasoning(fields, p1, c1, ws=ws))
     print(f"center  : {mn:8.3f} ms min {av:8.3f} avg  {n/mn/1e3:8.2f} Mprop/s  ({n} proposals)")
+    co = ops.center_reasoning(fields, p1, c1, ws=ws)
+    co = {"maxv": co[0].cpu(), "argmax": co[1].cpu(), "splits": co[2].cpu()}
+    if os.environ.get("KB_SAVE"):
+        torch.save(co, os.environ["KB_SAVE"] + ".center")
+    if os.environ.get("KB_CMP") and os.path.exists(os.environ["KB_CMP"] + ".center"):
+        ref = torch.load(os.environ["KB_CMP"] + ".center")
+        print("   vs saved: center outputs bit-equal", all(bool(torch.equal(ref[k], co[k])) for k in co))
 if which & {"all", "refine"}:
     rin, rc = st["refine_in_boxes"], st["refine_in"]
     rounds = int(st["refine_rounds"].sum())

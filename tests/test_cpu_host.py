@@ -110,7 +110,7 @@ def test_shard_ranges_cover_everything():
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from unmore_b200.sharding import shard_indices, pack_detections, gather_detections
+from unmore_b200.sharding import shard_indices, pack_rows_host, gather_rows, merge_rows, overflowed, rows_digest
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 n_images = 7
@@ -123,15 +123,23 @@ cap = 4
 boxes = torch.zeros((len(mine), cap, 4)); scores = torch.zeros((len(mine), cap)); counts = torch.zeros(len(mine), dtype=torch.int32)
 for j, i in enumerate(mine):
     b, s = fake(i); boxes[j, :len(b)] = b; scores[j, :len(b)] = s; counts[j] = len(b)
-rows = pack_detections(torch.tensor(mine), boxes, counts, scores)
-allrows = gather_detections(rows)
+big = 2 ** 40   # image ids beyond float32's 2^24 must survive the gather (ADVICE r1)
+rows = pack_rows_host(torch.tensor(mine) + big, boxes, counts, scores, max_rows=16)   # same capacity on every rank
+g = gather_rows(rows)                    # ONE all_gather_into_tensor
+assert g.shape == (world, 17, 6) and not bool(overflowed(g))
+merged, total = merge_rows(g)
+allrows = merged[: int(total)]
+allrows[:, 0] -= big
 ref = []
 for i in range(n_images):
     b, s = fake(i)
     for k in range(len(b)):
         ref.append(torch.cat([torch.tensor([float(i)]), b[k], s[k:k+1]]))
-ref = torch.stack(ref)
+ref = torch.stack(ref).to(torch.float64)
 assert allrows.shape == ref.shape and torch.equal(allrows, ref), (rank, allrows, ref)
+digests = [None] * world
+dist.all_gather_object(digests, rows_digest(allrows))
+assert len(set(digests)) == 1
 dist.destroy_process_group()
 print("ok", rank)
 """
@@ -176,3 +184,55 @@ def test_header_is_plain_c_and_links(tmp_path):
     cpp = tmp_path / "t.cpp"
     cpp.write_text('#include "unmore_b200.h"\nint main() { return unmore_version() < 0; }\n')
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-c", str(cpp), "-o", str(tmp_path / "t.o")], check=True)
+
+
+def _ast_signatures(path, class_name=None):
+    """{function name: [positional parameter names]} of a module (or one class of it) WITHOUT importing it."""
+    import ast
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    body = tree.body
+    if class_name is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name).body
+    out = {}
+    for n in body:
+        if isinstance(n, ast.FunctionDef):
+            a = n.args
+            names = [x.arg for x in a.posonlyargs + a.args]
+            n_def = len(a.defaults)
+            out[n.name] = (names, names[: len(names) - n_def] if n_def else names)
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference sources only exist in the build container")
+def test_mirror_signatures_match_the_reference():
+    """Every public method of the reference's Object_Discovery / Object_Scoring, batch_erode and
+    convert_pred_annotations_to_training_format exists here under the same name, with the reference's
+    parameters as a prefix in the same order, and can be called with exactly the reference's required
+    arguments (extra parameters here must be optional).  Read with ``ast``: nothing is imported."""
+    import inspect
+    from unmore_b200 import object_reasoning, object_scoring, post_process
+    from unmore_b200.utils import misc
+    pairs = [("/root/reference/object_reasoning.py", "Object_Discovery", object_reasoning.Object_Discovery),
+             ("/root/reference/object_scoring.py", "Object_Scoring", object_scoring.Object_Scoring)]
+    checked = 0
+    for path, cname, cls in pairs:
+        for name, (params, required) in _ast_signatures(path, cname).items():
+            assert hasattr(cls, name), f"{cname}.{name} missing"
+            sig = inspect.signature(getattr(cls, name))
+            ours = list(sig.parameters)
+            ref = [p for p in params if p != "self"]
+            mine = [p for p in ours if p != "self"]
+            if name == "get_prediction_with_proposal_images":   # a @staticmethod that still lists self in the reference
+                ref = [p for p in ref if p != "self"]
+            assert mine[: len(ref)] == ref, f"{cname}.{name}: {mine} vs reference {ref}"
+            for p in mine[len(ref):]:
+                assert sig.parameters[p].default is not inspect.Parameter.empty, f"{cname}.{name}: extra required parameter {p}"
+            checked += 1
+    for path, fn, ours in [("/root/reference/utils/misc.py", "batch_erode", misc.batch_erode),
+                           ("/root/reference/post_process.py", "convert_pred_annotations_to_training_format",
+                            post_process.convert_pred_annotations_to_training_format)]:
+        params, _ = _ast_signatures(path)[fn]
+        assert list(inspect.signature(ours).parameters)[: len(params)] == params, fn
+        checked += 1
+    assert checked >= 24

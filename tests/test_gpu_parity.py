@@ -568,3 +568,211 @@ def test_full_size_properties(dev, od, ops):
     ex = st["existence_scores"]
     assert bool(((ex >= 0) & (ex <= 1)).all())
     assert bool((st["pass1"] <= N).all()) and bool((st["refine_in"] <= 5 * N).all())
+
+
+# ------------------------------------------------------------------------------------------
+# the BENCHMARK workload under the oracle (configs[1]: anchors + random proposals, 4096 per image,
+# batched path) + trajectory-fork accounting
+# ------------------------------------------------------------------------------------------
+def fork_report(stats, b, dbg):
+    """Per-proposal comparison of the refine stage of batch entry ``b`` with the oracle's debug record:
+    returns (n_proposals, forks) where forks is a list of (index, kind, detail).  A fork is a proposal whose
+    final label differs, or whose final box is off by more than 1e-5 relative."""
+    n_in = int(stats["refine_in"][b])
+    lab = stats["refine_labels"][b, :n_in].cpu().numpy()
+    box = stats["refine_boxes"][b, :n_in].cpu().numpy()
+    forks = []
+    ref_lab = np.full(n_in, -2.0, np.float32)          # -2: left the list (area filter / zero box)
+    ref_box = np.zeros((n_in, 4), np.float32)
+    if "refine_index" in dbg and len(dbg["refine_out"]):
+        idx = dbg["refine_index"].numpy()
+        ref_lab[idx] = dbg["refine_labels"].numpy()
+        ref_box[idx] = dbg["refine_out"].numpy()
+    for k in range(n_in):
+        if lab[k] != ref_lab[k]:
+            forks.append((k, "label", (float(lab[k]), float(ref_lab[k]))))
+        elif lab[k] >= 0:
+            side = max(ref_box[k, 2] - ref_box[k, 0], ref_box[k, 3] - ref_box[k, 1])
+            rel = np.abs(box[k] - ref_box[k]) / np.maximum(np.abs(ref_box[k]), max(side, 1e-30))
+            if (rel > RTOL).any():
+                forks.append((k, "box", float(rel.max())))
+    return n_in, forks
+
+
+def test_bench_workload_vs_oracle(dev):
+    """Two full benchmark images (bench.py's generator: the 1225 anchors + 2871 random boxes = 4096 proposals,
+    480x640 fields) inside a 4-image batch through ReasoningPipeline.run_chunk — the exact call bench.py times —
+    against O.discover_image + O.score_image: lists / labels / masks exact, boxes / scores 1e-5.  Prints the
+    fork count of the 50-round trajectories (proposals whose final label or box differs from the oracle's)."""
+    from unmore_b200.pipeline import ReasoningPipeline
+    from unmore_b200.object_scoring import unpack_masks
+    H, W, N = 480, 640, 4096
+    ids = [0, 1, 2, 3]
+    check = [0, 3]
+    fields = torch.stack([synth.make_fields(i, H, W) for i in ids]).to(dev)
+    props_np = np.stack([synth.make_proposals(i, N, H, W) for i in ids])
+    anchors = synth.anchor_proposals(H, W)
+    assert np.array_equal(props_np[0, : len(anchors)], anchors)          # bench.py's layout: anchors first
+    assert np.array_equal(props_np[0, len(anchors):], synth.random_proposals(0, N - len(anchors), H, W))
+    pipe = ReasoningPipeline(dev)
+    st = {}
+    r = pipe.run_chunk(fields, torch.tensor(props_np, device=dev), stats=st)
+    args = O.make_args()
+    total_props = total_forks = 0
+    for b in check:
+        dbg = {}
+        ref = O.discover_image(fields[b].cpu(), props_np[b], args, debug=dbg)
+        n_in = int(st["refine_in"][b])
+        assert np.array_equal(st["refine_in_boxes"][b, :n_in].cpu().numpy(), dbg["refine_in"].numpy()), "refine inputs"
+        n, forks = fork_report(st, b, dbg)
+        total_props += n
+        total_forks += len(forks)
+        print(f"image {ids[b]}: {n} proposals enter the refine loop, {len(forks)} forks {forks[:5]}")
+        assert not forks, forks[:10]
+        k = int(r["box_counts"][b])
+        assert_boxes_close(r["boxes"][b, :k].cpu().numpy(), ref, f"discovered boxes, image {ids[b]}")
+        # scoring: feed the ORACLE's boxes to the oracle and the GPU's to the GPU (they agree to 1e-5; the
+        # masks depend on the snapped windows only, so they must still be bit-equal)
+        s_ref = O.score_image(fields[b].cpu(), ref.tolist(), args)
+        kk = int(r["keep_counts"][b])
+        assert kk == len(s_ref["score"])
+        keep = r["keep"][b, :kk].long()
+        assert np.array_equal(keep.cpu().numpy(), s_ref["nms_index"])
+        assert np.array_equal(r["bbox"][b, :kk].cpu().numpy(), s_ref["bbox"])
+        assert_rel(r["out"][b, :kk, 0].cpu().numpy(), s_ref["score"], "score")
+        assert np.array_equal(unpack_masks(r["masks"][b][keep], W), s_ref["masks"])
+        sel_ref = O.post_process_filter(s_ref["existence_score"], s_ref["center_score"], s_ref["boundary_score"], args)
+        assert np.array_equal(np.nonzero(r["selected"][b, :kk].cpu().numpy())[0], sel_ref)
+    print(f"bench-workload parity: {total_props} proposals x <=50 rounds, {total_forks} forks")
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_fuzz_parity_reduced(dev, cc):
+    """tests/tools/fuzz_parity.py, reduced: 12 (+8 with --analyze_cc) seeded scenes x 160 proposals, full
+    discovery + scoring against the oracle; forks are reported and must be zero."""
+    from unmore_b200.object_reasoning import Object_Discovery, default_args
+    from unmore_b200.object_scoring import Object_Scoring
+    od = Object_Discovery(default_args(analyze_cc=cc), device=dev)
+    sc = Object_Scoring(device=dev)
+    args = O.make_args(analyze_cc=cc)
+    n_det = n_forks = 0
+    for s in range(3000, 3000 + (8 if cc else 12)):
+        img = synth.make_fields(s)
+        props = synth.make_proposals(s, 160)
+        dbg = {}
+        ref = O.discover_image(img, props, args, debug=dbg)
+        st = {}
+        kb, kc = od.discover_batch(img.to(dev)[None].contiguous(), torch.tensor(props, device=dev)[None].contiguous(), stats=st)
+        n_in = int(st["refine_in"][0])
+        if "refine_in" in dbg:
+            assert np.array_equal(st["refine_in_boxes"][0, :n_in].cpu().numpy(), dbg["refine_in"].numpy()), s
+        _, forks = fork_report(st, 0, dbg)
+        n_forks += len(forks)
+        assert not forks, (s, forks[:5])
+        assert_boxes_close(kb[0, : int(kc[0])].cpu().numpy(), ref, f"seed {s}")
+        n_det += len(ref)
+        if len(ref):
+            s_ref = O.score_image(img, ref.tolist(), args)
+            anns = sc.score_image(img.to(dev), ref.astype(np.float64).tolist())
+            assert len(anns) == len(s_ref["score"]), s
+            assert np.array_equal(np.stack([a["segmentation"]["mask"] for a in anns]), s_ref["masks"]), s
+            assert_rel([a["score"] for a in anns], s_ref["score"], f"score, seed {s}")
+    print(f"fuzz cc={cc}: {n_det} detections, {n_forks} forks")
+
+
+def test_zero_argument_mains_write_reference_json(golden_dir, dev, tmp_path):
+    """main_object_discovery() / main_object_scoring() in the reference's zero-argument form
+    (object_reasoning.py:615-665, object_scoring.py:172-272) over a duck-typed dataset: the JSON files they
+    write reproduce the golden produced by running the reference's own mains (oracle/gen_golden.py gen_main_loop),
+    and the RLE segmentations decode to the masks of the in-memory form."""
+    import argparse, json
+    from unmore_b200 import rle
+    from unmore_b200.object_reasoning import FieldDataset, Object_Discovery
+    from unmore_b200.object_scoring import Object_Scoring
+    from unmore_b200.post_process import main as post_process_main
+    g = _load(golden_dir, "main_loop.npz")
+    H, W = int(g["H"]), int(g["W"])
+    ids = [int(i) for i in g["ids"]]
+    ds = FieldDataset([synth.make_fields(i, H, W) for i in ids], ids)
+    od = Object_Discovery(None, dev, test_dataset=ds, result_folder=str(tmp_path))
+    od.main_object_discovery()
+    with open(tmp_path / "discovery_results.json") as f:
+        disc = json.load(f)
+    for i in ids:
+        assert_boxes_close(np.asarray(disc.get(str(i), np.zeros((0, 4)))), g[f"disc_{i}"], f"image {i}")
+    sc = Object_Scoring(argparse.Namespace(raw_annotations_path=str(tmp_path / "discovery_results.json")), dev,
+                        test_dataset=ds, result_folder=str(tmp_path))
+    assert set(sc.raw_annotations) == set(disc)
+    sc.main_object_scoring()
+    with open(tmp_path / "object_discovery_with_scores.json") as f:
+        anns = json.load(f)
+    assert [a["image_id"] for a in anns] == g["ann_image_id"].tolist()
+    assert np.array_equal(np.array([a["bbox"] for a in anns], np.float32).reshape(-1, 4), g["ann_bbox"])
+    assert_rel([a["score"] for a in anns], g["ann_score"], "score")
+    dense = sc.main_object_scoring([f.to(dev) for f in ds.fields], ids)
+    for a, d in zip(anns, dense):
+        assert a["segmentation"]["size"] == [H, W]
+        assert np.array_equal(rle.decode(a["segmentation"]), d["segmentation"]["mask"])
+    out = post_process_main(["--pred_annotations_path", str(tmp_path / "object_discovery_with_scores.json")])
+    assert [a["id"] for a in out["annotations"]] == g["pp_ids"].tolist()
+    assert [a["image_id"] for a in out["annotations"]] == g["pp_image_id"].tolist()
+    assert (tmp_path / "selected_training_annotations.json").exists()
+
+
+def test_reference_named_helpers(golden_dir, dev, od):
+    """center_field_to_anti_center_map / unravel_index / binary_mask_to_tight_bbox_coco_style /
+    get_prediction_with_proposal_images under their reference names."""
+    from unmore_b200.object_scoring import Object_Scoring
+    g = _load(golden_dir, "units.npz")
+    am = od.center_field_to_anti_center_map(torch.tensor(g["a6_in"], device=dev))
+    assert np.allclose(am.cpu().numpy(), g["a6_out"], rtol=0, atol=1e-14)
+    assert od.unravel_index(130, (128, 128)) == (1, 2)
+    m = np.zeros((48, 70), np.uint8)
+    assert Object_Scoring.binary_mask_to_tight_bbox_coco_style(m) == [0.0, 0.0, 0.0, 0.0]
+    m[5:9, 33:65] = 1
+    assert Object_Scoring.binary_mask_to_tight_bbox_coco_style(m) == [33.0, 5.0, 32.0, 4.0]
+    tiles = torch.rand((3, 4, 128, 128), device=dev)
+    sdf, cen = od.get_prediction_with_proposal_images(tiles)
+    assert torch.equal(sdf, tiles[:, 0]) and torch.equal(cen, tiles[:, 1:3])
+
+
+def test_analyze_cc_more_components_than_the_device_buffer(dev):
+    """a passing proposal whose union mask has more 8-connected components than unmore_cc_cap()
+    (speckled masks) must be handled like the reference (any number of components, object_reasoning.py:207-256),
+    not abort the batch: center_reasoning, discover_batch and separate_connected_components vs the oracle."""
+    from unmore_b200 import _lib
+    from unmore_b200.object_reasoning import Object_Discovery, default_args
+    cap = _lib.load().unmore_cc_cap()
+    H, W = 480, 640
+    f = torch.zeros((4, H, W), dtype=torch.float32)
+    f[0] = -1.0                      # boundary-distance field: background
+    f[3] = 1.0                       # existence: everything passes the check
+    n_blobs = 0
+    for by in range(6):
+        for bx in range(7):
+            y, x = 110 + 30 * by, 105 + 28 * bx
+            f[0, y:y + 7, x:x + 8] = 1.0
+            n_blobs += 1
+    assert n_blobs > cap
+    props = np.array([[100.0, 100.0, 310.0, 300.0],      # all 42 blobs: > cap components
+                      [100.0, 100.0, 200.0, 180.0],      # a few blobs: < cap
+                      [0.0, 0.0, 60.0, 60.0]])           # nothing
+    args = O.make_args(analyze_cc=True)
+    odc = Object_Discovery(default_args(analyze_cc=True), device=dev)
+    ref = O.center_reasoning(f, torch.tensor(props), args, return_debug=True)
+    from scipy.ndimage import label
+    assert label(ref["union"][0].numpy(), np.ones((3, 3), int))[1] > cap
+    cr = odc.center_reasoning(f.to(dev), props)
+    assert np.array_equal(cr["proposals_pass_singularity"].cpu().numpy(), ref["proposals_pass_singularity"].numpy())
+    assert np.array_equal(cr["splited_new_proposals"].cpu().numpy(), ref["splited_new_proposals"].numpy())
+    comb, ind = Object_Discovery.separate_connected_components(ref["union"].to(dev))
+    rc, ri = O.separate_connected_components(ref["union"])
+    assert ind == ri and comb["multi"] == rc["multi"] and comb["single"] == rc["single"]
+    det = odc.discover_image(f.to(dev), props)
+    assert_boxes_close(det, O.discover_image(f, props, args), "discovery with > cap components")
+    # batched: the overflowing image sits next to a normal one
+    f2 = torch.stack([f, synth.make_fields(5)]).to(dev)
+    p2 = torch.tensor(np.stack([np.concatenate([props, props[:1]]), synth.make_proposals(5, 4)]), device=dev)
+    kb, kc = odc.discover_batch(f2, p2)
+    assert_boxes_close(kb[0, : int(kc[0])].cpu().numpy(), O.discover_image(f, np.concatenate([props, props[:1]]), args), "batch[0]")
+    assert_boxes_close(kb[1, : int(kc[1])].cpu().numpy(), O.discover_image(synth.make_fields(5), synth.make_proposals(5, 4), args), "batch[1]")

@@ -31,7 +31,8 @@ SIGNATURES = {
     "unmore_box_nms_matrix": [_p, _p, _i, _f, _p, _p, _p, _p, _p],
     "unmore_score_and_rasterise": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
     "unmore_mask_resize": [_p, _i, _i, _i, _i, _i, _p, _p],
-    "unmore_final_scores": [_p, _p, _p, _p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p],
+    "unmore_final_scores": [_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _p, _p, _p, _p],
+    "unmore_pack_detections": [_p, _p, _p, _p, _i, _i, _p, _i, _p],
     "unmore_sat_build": [_p, _i, _i, _i, _p, _p],
     "unmore_sat_build_fields": [_p, _i, _i, _i, _i, _p, _i, _p, _p],
     "unmore_box_sums": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p],

@@ -68,6 +68,14 @@ void anti_center_filter(double* filt) {
 
 int check_fields(const float* f, int n_img, int C, int H, int W) {
   if (!f || n_img <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(UNMORE_E_INVALID, "bad field tensor");
+  // the kernels are launched on the CURRENT device: a field stack that lives on another GPU would be read
+  // through a foreign pointer (illegal address, or silent peer traffic) — refuse it instead
+  cudaPointerAttributes attr;
+  int dev = -1;
+  if (cudaPointerGetAttributes(&attr, f) == cudaSuccess && attr.type == cudaMemoryTypeDevice &&
+      cudaGetDevice(&dev) == cudaSuccess && attr.device != dev)
+    return fail(UNMORE_E_INVALID, "field tensor lives on device %d but the current device is %d (set the device, or use the stream of the tensor's device)", attr.device, dev);
+  (void)cudaGetLastError();
   return 0;
 }
 
@@ -258,8 +266,8 @@ int unmore_mask_resize(const unsigned char* masks, int B, int H, int W, int out_
 }
 
 int unmore_final_scores(const float* scores, const float* tight, const int* areas, const int* keep,
-                        const int* keep_counts, int cap, int n_img, float existence_score_thres, float center_score_thres,
-                        float boundary_score_thres, double* out, float* bbox_xywh_out, unsigned char* selected_out,
+                        const int* keep_counts, int cap, int n_img, double existence_score_thres, double center_score_thres,
+                        double boundary_score_thres, double* out, float* bbox_xywh_out, unsigned char* selected_out,
                         unmore_stream_t stream) {
   if (!scores || !tight || !areas || !keep || !keep_counts || !out || !bbox_xywh_out || cap < 0 || n_img < 0)
     return fail(UNMORE_E_INVALID, "unmore_final_scores: bad argument");
@@ -269,6 +277,15 @@ int unmore_final_scores(const float* scores, const float* tight, const int* area
   p.existence_thres = existence_score_thres; p.center_thres = center_score_thres; p.boundary_thres = boundary_score_thres;
   p.out = out; p.bbox_xywh = reinterpret_cast<float4*>(bbox_xywh_out); p.selected = selected_out;
   return cuda_fail(launch_final_scores(p, (cudaStream_t)stream), "final_scores_kernel");
+}
+
+int unmore_pack_detections(const long long* image_ids, const float* bbox_xywh, const double* out5, const int* keep_counts,
+                           int cap, int n_img, double* rows, int max_rows, unmore_stream_t stream) {
+  if (!image_ids || !bbox_xywh || !out5 || !keep_counts || !rows || cap < 0 || n_img < 0 || max_rows < 0)
+    return fail(UNMORE_E_INVALID, "unmore_pack_detections: bad argument");
+  return cuda_fail(launch_pack_detections(image_ids, reinterpret_cast<const float4*>(bbox_xywh), out5, keep_counts, cap, n_img,
+                                          rows, max_rows, (cudaStream_t)stream),
+                   "pack_detections_kernel");
 }
 
 int unmore_sat_build(const float* in, int n_planes, int H, int W, double* out, unmore_stream_t stream) {

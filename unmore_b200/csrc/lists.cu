@@ -126,4 +126,69 @@ int launch_compact(const CompactParams& p, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// ---- detection rows for the end-of-run collective ----------------------------------------------------
+// Appends the detections of a batch — (image_id, x, y, w, h, score) as six doubles per row, image-major, in
+// the order of the scoring NMS — to a fixed-capacity row buffer that is handed to the all-gather as it is:
+// rows[0] = (row count, overflow flag, 0, 0, 0, 0) is the header, rows[1 ..] the detections.  The cursor
+// lives in the header, so consecutive batches on one stream append without a host round trip, and the
+// image ids travel as doubles (exact to 2^53; the float32 column of the round-1 gather collided above 2^24).
+// One CTA: a batch holds a few thousand detections.
+__global__ void __launch_bounds__(1024) pack_detections_kernel(const long long* __restrict__ image_ids,
+                                                              const float4* __restrict__ bbox_xywh,
+                                                              const double* __restrict__ out5,
+                                                              const int* __restrict__ keep_counts, int cap, int n_img,
+                                                              double* __restrict__ rows, int max_rows) {
+  __shared__ int carry;
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = (int)rows[0];
+  __syncthreads();
+  for (int base = 0; base < n_img; base += blockDim.x) {
+    const int b = base + threadIdx.x;
+    const int n = b < n_img ? min(keep_counts[b], cap) : 0;
+    int x = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(kFullMask, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int s = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, s, o);
+        if (lane >= o) s += y;
+      }
+      wsum[lane] = s;
+    }
+    __syncthreads();
+    const int first = carry + (warp ? wsum[warp - 1] : 0) + x - n;   // rows before this image
+    for (int i = 0; i < n; ++i) {
+      const int r = first + i;
+      if (r >= max_rows) break;
+      const size_t src = (size_t)b * cap + i;
+      const float4 bx = bbox_xywh[src];
+      double* o = rows + (size_t)(r + 1) * 6;
+      o[0] = (double)image_ids[b]; o[1] = (double)bx.x; o[2] = (double)bx.y; o[3] = (double)bx.z; o[4] = (double)bx.w;
+      o[5] = out5[src * 5];
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = first + n;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (carry > max_rows) { rows[1] = 1.0; carry = max_rows; }
+    rows[0] = (double)carry;
+  }
+}
+
+int launch_pack_detections(const long long* image_ids, const float4* bbox_xywh, const double* out5, const int* keep_counts,
+                           int cap, int n_img, double* rows, int max_rows, cudaStream_t stream) {
+  if (n_img <= 0) return 0;
+  pack_detections_kernel<<<1, 1024, 0, stream>>>(image_ids, bbox_xywh, out5, keep_counts, cap, n_img, rows, max_rows);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace unmore

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) final_scores_kernel(const FinalParams p) 
     o[4] = area_score;                // area_score
     p.bbox_xywh[dst] = make_float4(t.x, t.y, __fsub_rn(t.z, t.x), __fsub_rn(t.w, t.y));
     if (p.selected)
-      p.selected[dst] = !(s.x < p.existence_thres || s.y < p.center_thres || s.z < p.boundary_thres) ? 1 : 0;
+      p.selected[dst] = !((double)s.x < p.existence_thres || (double)s.y < p.center_thres || (double)s.z < p.boundary_thres) ? 1 : 0;
   }
 }
 

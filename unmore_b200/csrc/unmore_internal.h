@@ -103,6 +103,8 @@ struct CompactParams {
   int n_img;
 };
 int launch_compact(const CompactParams& p, cudaStream_t stream);
+int launch_pack_detections(const long long* image_ids, const float4* bbox_xywh, const double* out5, const int* keep_counts,
+                           int cap, int n_img, double* rows, int max_rows, cudaStream_t stream);
 
 // ---- nms.cu --------------------------------------------------------------------------
 struct NmsParams {
@@ -142,7 +144,7 @@ struct FinalParams {
   const int* keep;       // [n_img, cap] indices kept by NMS, in order
   const int* keep_counts;
   int cap, n_img;
-  float existence_thres, center_thres, boundary_thres;  // post_process.py:38-40
+  double existence_thres, center_thres, boundary_thres;  // post_process.py:38-40 (Python floats: the fp32 scores are compared in double, :64-69)
   double* out;           // [n_img, cap, 5] (score, existence, center, boundary, area_score) in keep order
   float4* bbox_xywh;     // [n_img, cap] COCO-style box in keep order
   unsigned char* selected;  // nullable [n_img, cap] post_process predicate

@@ -14,6 +14,8 @@ device-side counts, no host round-trips between stages.
 from __future__ import annotations
 
 import argparse
+import json
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -33,8 +35,44 @@ def default_args(**over) -> argparse.Namespace:
     return argparse.Namespace(**d)
 
 
+def _label_boxes_host(mask_u8: np.ndarray):
+    """8-connected components of one [128,128] mask on the host, in scipy's label order, as
+    [x_start, y_start, x_stop, y_stop] slice bounds — the overflow path of separate_connected_components
+    (more components than the kernels' per-proposal box buffer, unmore_cc_cap())."""
+    from scipy.ndimage import find_objects, label
+    lab, n = label(mask_u8, np.ones((3, 3), dtype=np.int64))
+    return [[sl[1].start, sl[0].start, sl[1].stop, sl[0].stop] for sl in find_objects(lab)][:n]
+
+
+class FieldDataset:
+    """Duck-typed stand-in for the reference's ``COCO_Dataset`` on this path (datasets.py:441-453): the
+    field stacks the producer made, addressed by position.  ``get_image_with_index(i)`` returns
+    ``(fields [4,H,W] fp32, {'image_id': tensor})`` exactly like the reference's accessor returns the RGB
+    image; ``start_idx`` / ``end_idx`` select a contiguous range like datasets.py:432-435."""
+
+    def __init__(self, fields, image_ids=None, start_idx: int = -1, end_idx: int = -1):
+        n = len(fields)
+        ids = list(range(n)) if image_ids is None else [int(i) for i in image_ids]
+        sel = range(n) if (start_idx == -1 or end_idx == -1) else range(n)[start_idx:end_idx]
+        self.fields = fields
+        self.index = list(sel)
+        self.image_ids = ids
+
+    def __len__(self):
+        return len(self.index)
+
+    def get_image_with_index(self, index):
+        k = self.index[index]
+        return self.fields[k], {"image_id": torch.tensor(self.image_ids[k])}
+
+
 class Object_Discovery:
-    def __init__(self, args: Optional[argparse.Namespace] = None, device=None, channels: ops.Channels = ops.DEFAULT_CHANNELS):
+    def __init__(self, args: Optional[argparse.Namespace] = None, device=None, channels: ops.Channels = ops.DEFAULT_CHANNELS,
+                 test_dataset=None, result_folder: Optional[str] = None):
+        """Reference: ``Object_Discovery(args, device)`` (object_reasoning.py:44-107).  The reference builds its
+        nets and a COCO_Dataset from ``args``; here the producer is outside the path, so the dataset of field
+        stacks (anything with ``__len__`` / ``get_image_with_index``, e.g. ``FieldDataset``) and the result
+        folder are handed in (or assigned to ``self.test_dataset`` / ``self.result_folder`` afterwards)."""
         self.args = args if args is not None else default_args()
         for k, v in HYPER_DEFAULTS.items():
             if not hasattr(self.args, k):
@@ -45,12 +83,38 @@ class Object_Discovery:
         self.channels = channels
         self.height = None
         self.width = None
+        self.test_dataset = test_dataset
+        self.result_folder = result_folder
 
     # ---- a1 ---------------------------------------------------------------------------
     @staticmethod
     def generate_random_proposal(height, width):
         """object_reasoning.py:110-137 — float64 [N,4] anchors (host side, negligible cost)."""
         return anchor_proposals(height, width)
+
+    @staticmethod
+    def unravel_index(index, shape):
+        """object_reasoning.py:199-204 (host integer arithmetic; the kernel does the same split of the
+        flat arg-max into (yc, xc), center.cu)."""
+        out = []
+        for dim in reversed(shape):
+            out.append(index % dim)
+            index = index // dim
+        return tuple(reversed(out))
+
+    def center_field_to_anti_center_map(self, vote_maps, kernel_size=5):
+        """object_reasoning.py:360-377 — [B,2,H,W] center fields -> [B,H,W] float64 anti-center map
+        (5x5 cross-correlation with the normalised offset filter, zero padding, / (k*k-1))."""
+        if kernel_size != 5:
+            raise ValueError("the CUDA anti-center map implements the reference's hard-coded kernel_size=5 (:533)")
+        return ops.anti_center_map(torch.as_tensor(vote_maps).to(self.device), kernel_size)
+
+    def get_prediction_with_proposal_images(self, proposal_images):
+        """object_reasoning.py:339-358 under the field-stub bridge: ``proposal_images`` are already-cropped
+        [N,C,128,128] field tiles, the 'net' selects channels -> (sdf_maps [N,128,128], center_fields [N,2,128,128])."""
+        t = torch.as_tensor(proposal_images).to(self.device, torch.float32)
+        ch = self.channels
+        return t[:, ch.sdf], torch.stack((t[:, ch.center_row], t[:, ch.center_col]), dim=1)
 
     # ---- helpers ----------------------------------------------------------------------
     def _fields(self, image: torch.Tensor) -> torch.Tensor:
@@ -103,23 +167,62 @@ class Object_Discovery:
             # (:561-572) enlarged component boxes of passing multi-component masks, appended after the splits
             counts, cboxes, overflow = cc
             if int(overflow.item()):
-                raise RuntimeError("a proposal has more connected components than unmore_cc_cap()")
-            valid = torch.arange(cboxes.shape[2], device=self.device)[None, :] < counts[0][:, None].to(torch.long)
-            new = torch.cat((new, cboxes[0][valid]), dim=0)
+                f = self._fields(image)
+                extra = self._cc_boxes_with_overflow(f, boxes, torch.nonzero(~fail).flatten().tolist(), counts[0], cboxes[0],
+                                                     f.shape[-2], f.shape[-1])
+                new = torch.cat((new, torch.as_tensor(extra, device=self.device)), dim=0)
+            else:
+                valid = torch.arange(cboxes.shape[2], device=self.device)[None, :] < counts[0][:, None].to(torch.long)
+                new = torch.cat((new, cboxes[0][valid]), dim=0)
         return {"proposals_pass_singularity": boxes[0][~fail], "splited_new_proposals": new}
+
+    def _union_masks(self, fields: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        """Un-eroded union masks (object_reasoning.py:528-531) of ``boxes`` [1,K,4] as [K,128,128] u8, from the
+        bit-exact resized crops and the same thresholds the center kernel applies (common.cuh)."""
+        ch = self.channels
+        crops = ops.crop_resize(fields, boxes.contiguous(), [ch.sdf, ch.center_row, ch.center_col])[0]
+        sq = crops[:, 1] * crops[:, 1] + crops[:, 2] * crops[:, 2]
+        return ((crops[:, 0] > 8.94069671630859375e-08) | (sq > 0.2500000298023223876953125)).to(torch.uint8)
+
+    def _cc_boxes_with_overflow(self, fields, boxes, passing_idx, cc_counts, cc_boxes, H, W):
+        """Component boxes (enlarged, :561-572) of the passing proposals ``passing_idx`` of ONE image, in
+        proposal order.  Proposals whose component count reached the device buffer (unmore_cc_cap()) are
+        re-labelled on the host without a limit, so any number of components is handled like the reference
+        (object_reasoning.py:207-256) — only those rare proposals leave the device."""
+        cap = cc_boxes.shape[1]
+        counts = cc_counts.cpu().numpy()
+        dev_boxes = cc_boxes.cpu().numpy()
+        full = [int(k) for k in passing_idx if counts[k] >= cap]
+        host = {}
+        if full:
+            masks = self._union_masks(fields, boxes[:, full]).cpu().numpy()
+            for k, m in zip(full, masks):
+                bb = _label_boxes_host(m)
+                host[k] = np.asarray(self.enlarge_proposals(bb, (H, W), 1.5), dtype=np.float64).reshape(-1, 4)
+        out = []
+        for k in passing_idx:
+            k = int(k)
+            if k in host:
+                if len(host[k]) >= 2:
+                    out.append(host[k])
+            elif counts[k]:
+                out.append(dev_boxes[k, : counts[k]])
+        return np.concatenate(out, axis=0) if out else np.zeros((0, 4), np.float64)
 
     @staticmethod
     def separate_connected_components(binary_masks):
         """object_reasoning.py:207-256 — ({'single': [...], 'multi': [...]}, indicators) with bboxes
         [x_start, y_start, x_stop, y_stop]; labelling on the GPU (8-connected, scipy label order)."""
-        counts, boxes = ops.connected_components((binary_masks != 0).to(torch.uint8))
+        m8 = (binary_masks != 0).to(torch.uint8)
+        counts, boxes = ops.connected_components(m8)
         counts, boxes = counts.cpu().tolist(), boxes.cpu().tolist()
         cap = len(boxes[0]) if boxes else 0
         combined = {"single": [], "multi": []}
         indicators = []
-        for n, bb in zip(counts, boxes):
-            if n > cap:
-                raise RuntimeError("a mask has more connected components than unmore_cc_cap()")
+        for i, (n, bb) in enumerate(zip(counts, boxes)):
+            if n > cap:   # more components than the device buffer holds: label this one mask on the host
+                bb = _label_boxes_host(m8[i].cpu().numpy())
+                n = len(bb)
             if n == 1:
                 combined["single"].append(bb[0])
                 indicators.append(1)
@@ -243,8 +346,25 @@ class Object_Discovery:
             lost = torch.zeros((1,), dtype=torch.int32, device=dev)
             ops.compact_boxes(cc_boxes, c1, ops.MODE_U8_NONZERO, cc_counts, group=cc_boxes.shape[2], out=split,
                               counts_out=sc, append=True, group_counts=cc_counts, overflow=lost)
-            if int(cc_over.item()) or int(lost.item()):   # one sync per batch, only with --analyze_cc
-                raise RuntimeError("analyze_cc: component boxes exceeded unmore_cc_cap() or the split-list capacity")
+            if int(lost.item()):   # one sync per batch, only with --analyze_cc
+                raise RuntimeError("analyze_cc: component boxes exceeded the split-list capacity")
+            if int(cc_over.item()):
+                # a proposal with more components than the device buffer (unmore_cc_cap()): rebuild the component
+                # part of the split list of the affected images with the unlimited host labelling (rare path)
+                c1h = c1.cpu().tolist()
+                capc = cc_boxes.shape[2]
+                for b in range(B):
+                    n = c1h[b]
+                    if n == 0 or int((cc_counts[b, :n] >= capc).sum()) == 0:
+                        continue
+                    passing = torch.nonzero(am1[b, :n] < 0).flatten().tolist()
+                    extra = self._cc_boxes_with_overflow(fields[b:b + 1], p1[b:b + 1], passing, cc_counts[b], cc_boxes[b],
+                                                         fields.shape[-2], fields.shape[-1])
+                    n_split = 4 * int((am1[b, :n] >= 0).sum())
+                    if n_split + len(extra) > split_cap:
+                        raise RuntimeError("analyze_cc: component boxes exceeded the split-list capacity")
+                    split[b, n_split:n_split + len(extra)] = torch.as_tensor(extra, device=dev)
+                    sc[b] = n_split + len(extra)
         # re-check the split proposals (:639-646)
         ex2 = ops.existence_scores(fields, split, sc, ch=ch, ws=ws)
         p2, c2, _ = ops.compact_boxes(split, sc, ops.MODE_SCORE_GE, ex2, thr=a.class_score_thres, out_dtype=f64)
@@ -270,12 +390,32 @@ class Object_Discovery:
                          refine_in_boxes=refine_in, pass1_boxes=p1, argmax1=am1)
         return kb, kc
 
-    def main_object_discovery(self, images, image_ids, proposals=None) -> Dict[int, np.ndarray]:
-        """object_reasoning.py:615-665 over an in-memory list of field stacks: returns
-        ``results_dict`` {image_id: [K,4] fp32}; images with no detection are absent."""
+    def main_object_discovery(self, images=None, image_ids=None, proposals=None) -> Dict[int, np.ndarray]:
+        """object_reasoning.py:615-665.  Called with no arguments like the reference: loops over
+        ``self.test_dataset`` (``get_image_with_index`` -> field stack + ``{'image_id'}``), runs the loop body
+        for every image and dumps ``results_dict`` {image_id: [[x1,y1,x2,y2], ...]} to
+        ``<result_folder>/discovery_results.json`` (:664-665); images with no detection are absent, as in the
+        reference.  ``images`` / ``image_ids`` (not in the reference) run the same loop over in-memory stacks
+        without touching the disk.  Returns ``results_dict`` (the reference returns None)."""
+        from . import rle
         results = {}
-        for img, iid in zip(images, image_ids):
-            det = self.discover_image(img, proposals)
+        if images is not None:
+            for img, iid in zip(images, image_ids):
+                det = self.discover_image(img, proposals)
+                if len(det):
+                    results[int(iid)] = det
+            return results
+        if self.test_dataset is None:
+            raise RuntimeError("main_object_discovery(): set self.test_dataset (e.g. FieldDataset) first")
+        for image_idx in range(0, len(self.test_dataset)):
+            image, label = self.test_dataset.get_image_with_index(image_idx)
+            image_id = int(label["image_id"].item()) if torch.is_tensor(label["image_id"]) else int(label["image_id"])
+            self.height, self.width = image.shape[-2], image.shape[-1]
+            det = self.discover_image(image, proposals)
             if len(det):
-                results[int(iid)] = det
+                results[image_id] = det
+        if self.result_folder is not None:
+            os.makedirs(self.result_folder, exist_ok=True)
+            with open(os.path.join(self.result_folder, "discovery_results.json"), "w") as f:
+                f.write(rle.discovery_results_json(results))
         return results

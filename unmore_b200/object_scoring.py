@@ -8,6 +8,8 @@ x) — the reference's dense [K, H, W] float canvases are never materialised."""
 from __future__ import annotations
 
 import argparse
+import json
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -27,7 +29,10 @@ def unpack_masks(packed: torch.Tensor, width: int) -> np.ndarray:
 
 class Object_Scoring:
     def __init__(self, args: Optional[argparse.Namespace] = None, device=None, raw_annotations: Optional[dict] = None,
-                 channels: ops.Channels = ops.DEFAULT_CHANNELS):
+                 channels: ops.Channels = ops.DEFAULT_CHANNELS, test_dataset=None, result_folder: Optional[str] = None):
+        """Reference: ``Object_Scoring(args, device)`` (object_scoring.py:45-104); dataset and result folder
+        are handed in like in ``Object_Discovery``.  ``args.raw_annotations_path`` is read by
+        ``load_raw_annotations`` when ``raw_annotations`` is not given."""
         self.args = args if args is not None else argparse.Namespace()
         for k, v in POST_DEFAULTS.items():
             if not hasattr(self.args, k):
@@ -37,6 +42,16 @@ class Object_Scoring:
             raise RuntimeError("unmore_b200 has no CPU path; pass a CUDA device")
         self.channels = channels
         self.raw_annotations = raw_annotations if raw_annotations is not None else {}
+        self.test_dataset = test_dataset
+        self.result_folder = result_folder
+        if raw_annotations is None and getattr(self.args, "raw_annotations_path", None):
+            self.load_raw_annotations()
+
+    def load_raw_annotations(self):
+        """object_scoring.py:106-110 — reads ``discovery_results.json`` ({image_id: [[x1,y1,x2,y2], ...]})."""
+        with open(self.args.raw_annotations_path) as f:
+            self.raw_annotations = json.load(f)
+        return self.raw_annotations
 
     def _fields(self, image):
         f = image.to(self.device, torch.float32)
@@ -65,6 +80,19 @@ class Object_Scoring:
                                           self.args.center_score_thres, self.args.boundary_score_thres)
         return dict(out=out, bbox=bbox, selected=sel, keep=keep, keep_counts=kc, masks=masks, areas=areas, tight=tight,
                     scores=scores)
+
+    @staticmethod
+    def binary_mask_to_tight_bbox_coco_style(binary_mask):
+        """object_scoring.py:160-164 (pycocotools encode + toBbox) for one dense [H, W] mask:
+        [xmin, ymin, xmax - xmin + 1, ymax - ymin + 1] as floats, zeros for an empty mask.  Packs the mask and
+        takes the extent on the GPU (``unmore_mask_stats``: __ffs / __clz on the packed rows)."""
+        m = torch.as_tensor(np.asarray(binary_mask.cpu() if torch.is_tensor(binary_mask) else binary_mask)).to(torch.uint8)
+        packed = ops.mask_pack(m.cuda()[None].contiguous())
+        areas, tight = ops.mask_stats(packed, m.shape[1])
+        if int(areas[0]) == 0:
+            return [0.0, 0.0, 0.0, 0.0]
+        x1, y1, x2, y2 = (float(v) for v in tight[0].cpu().tolist())
+        return [x1, y1, x2 - x1, y2 - y1]   # mask_stats reports exclusive upper bounds (xmax + 1, ymax + 1)
 
     @staticmethod
     def binary_mask_to_rle(binary_mask):
@@ -103,12 +131,32 @@ class Object_Scoring:
             anns.append(ann)
         return anns
 
-    def main_object_scoring(self, images, image_ids) -> List[dict]:
-        """object_scoring.py:172-272 over in-memory field stacks; returns ``out_annotations``."""
+    def main_object_scoring(self, images=None, image_ids=None) -> List[dict]:
+        """object_scoring.py:172-272.  Called with no arguments like the reference: loops over
+        ``self.test_dataset``, skips images without raw predictions (:177-179), and dumps ``out_annotations``
+        (``segmentation`` = COCO RLE dicts, :257-268) to ``<result_folder>/object_discovery_with_scores.json``.
+        ``images`` / ``image_ids`` (not in the reference) run the loop over in-memory stacks and keep the masks
+        dense.  Returns ``out_annotations`` (the reference returns None)."""
+        from . import rle
         out = []
-        for img, iid in zip(images, image_ids):
-            raw = self.raw_annotations.get(str(int(iid)))
-            if raw is None:
+        if images is not None:
+            for img, iid in zip(images, image_ids):
+                raw = self.raw_annotations.get(str(int(iid)))
+                if raw is None:
+                    continue
+                out.extend(self.score_image(img, raw, image_id=int(iid)))
+            return out
+        if self.test_dataset is None:
+            raise RuntimeError("main_object_scoring(): set self.test_dataset (e.g. FieldDataset) first")
+        for image_idx in range(0, len(self.test_dataset)):
+            image, label = self.test_dataset.get_image_with_index(image_idx)
+            image_id = int(label["image_id"].item()) if torch.is_tensor(label["image_id"]) else int(label["image_id"])
+            if str(image_id) not in self.raw_annotations.keys():
+                print(image_id, "do not have raw predictions")
                 continue
-            out.extend(self.score_image(img, raw, image_id=int(iid)))
+            out.extend(self.score_image(image, self.raw_annotations[str(image_id)], image_id=image_id, rle=True))
+        if self.result_folder is not None:
+            os.makedirs(self.result_folder, exist_ok=True)
+            with open(os.path.join(self.result_folder, "object_discovery_with_scores.json"), "w") as f:
+                f.write(rle.scored_annotations_json(out))
         return out

@@ -26,8 +26,20 @@ class Channels:
 DEFAULT_CHANNELS = Channels()
 
 
+_device = None   # device of the call being assembled: set by _on(), consumed by _stream() / _call()
+
+
+def _on(t: torch.Tensor):
+    """Pins the device of the call being assembled to the device of its first tensor (the C ABI
+    launches on the CURRENT device; without this, tensors on cuda:1 under a current device of cuda:0 would be
+    dereferenced by a kernel running on GPU 0)."""
+    global _device
+    _device = t.device
+    return t
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(_device).cuda_stream
 
 
 class StageTimer:
@@ -39,7 +51,7 @@ class StageTimer:
         self.launches = 0
 
     def record(self, name, kernels, fn, *args):
-        st = torch.cuda.current_stream()
+        st = torch.cuda.current_stream(_device)
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
         a.record(st)
@@ -66,7 +78,8 @@ _KERNELS = {"unmore_crop_resize": 1, "unmore_existence_scores": 1, "unmore_cente
             "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
             "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_connected_components": 1, "unmore_box_nms_matrix": 3,
             "unmore_score_and_rasterise": 1, "unmore_mask_resize": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
-            "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3, "unmore_mask_rle_counts": 1}
+            "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3, "unmore_mask_rle_counts": 1,
+            "unmore_pack_detections": 1}
 
 
 def set_timer(t: Optional[StageTimer]):
@@ -75,13 +88,20 @@ def set_timer(t: Optional[StageTimer]):
 
 
 def _call(name, *args, counts=None):
-    global LAUNCHES
+    global LAUNCHES, _device
     k = _KERNELS[name] + (1 if counts is not None else 0)
     LAUNCHES += k
-    if _timer is not None:
-        _timer.record(name, k, _lib.call, *args)
-    else:
-        _lib.call(name, *args)
+    dev = _device
+    try:
+        if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                _lib.call(name, *args) if _timer is None else _timer.record(name, k, _lib.call, *args)
+        elif _timer is not None:
+            _timer.record(name, k, _lib.call, *args)
+        else:
+            _lib.call(name, *args)
+    finally:
+        _device = None
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -93,6 +113,7 @@ def _check_fields(fields: torch.Tensor) -> Tuple[int, int, int, int]:
         raise _lib.UnmoreError("fields must live on a CUDA device (no CPU path)")
     if fields.dtype != torch.float32 or fields.dim() != 4 or not fields.is_contiguous():
         raise _lib.UnmoreError("fields must be contiguous fp32 [n_img, C, H, W]")
+    _on(fields)
     return tuple(fields.shape)  # type: ignore[return-value]
 
 
@@ -186,7 +207,7 @@ def boundary_refine(fields, boxes, counts=None, n_round: int = 50, apply_small_f
 def update_bbox_from_tiles(tiles: torch.Tensor):
     if not tiles.is_cuda or tiles.dtype != torch.float32 or tiles.dim() != 3 or tiles.shape[1:] != (CROP, CROP):
         raise _lib.UnmoreError("tiles must be CUDA fp32 [M, 128, 128]")
-    tiles = tiles.contiguous()
+    tiles = _on(tiles.contiguous())
     m = tiles.shape[0]
     deltas = torch.zeros((m, 4), dtype=torch.float32, device=tiles.device)
     mx = torch.zeros((m,), dtype=torch.float32, device=tiles.device)
@@ -200,7 +221,7 @@ MODE_FLAGS, MODE_SCORE_GE, MODE_LABEL_EQ, MODE_ARGMAX_GE0, MODE_ARGMAX_LT0, MODE
 def compact_boxes(inp, counts_in, mode, pred, thr=0.0, group=1, out=None, counts_out=None, cap_out=None,
                   out_dtype=None, append=False, want_index=False, group_counts=None, overflow=None):
     """Stable per-image selection; returns (out [n_img, cap_out, 4], counts_out [n_img], index or None)."""
-    dev = inp.device
+    dev = _on(inp).device
     n_img, cap_in = inp.shape[0], inp.shape[1]
     if group != 1 and inp.shape[2] != group:
         raise _lib.UnmoreError("compact_boxes: input must be [n_img, cap, group, 4]")
@@ -223,7 +244,7 @@ def box_nms(boxes, scores=None, counts=None, iou_threshold: float = 0.5, want_bo
     if not boxes.is_cuda or boxes.dtype != torch.float32 or boxes.dim() != 3 or not boxes.is_contiguous():
         raise _lib.UnmoreError("boxes must be contiguous CUDA fp32 [n_img, cap, 4]")
     n_img, cap = boxes.shape[0], boxes.shape[1]
-    dev = boxes.device
+    dev = _on(boxes).device
     keep = torch.full((n_img, cap), -1, dtype=torch.int32, device=dev)
     kc = torch.zeros((n_img,), dtype=torch.int32, device=dev)
     order = torch.empty((n_img, max(cap, 1)), dtype=torch.int32, device=dev)
@@ -237,7 +258,7 @@ def box_nms(boxes, scores=None, counts=None, iou_threshold: float = 0.5, want_bo
 
 def box_nms_matrix(boxes, scores=None, iou_threshold: float = 0.5):
     """One list of K boxes [K,4] fp32 -> kept indices (int64, descending-score order)."""
-    boxes = boxes.contiguous().to(torch.float32)
+    boxes = _on(boxes.contiguous().to(torch.float32))
     K = boxes.shape[0]
     dev = boxes.device
     nblk = (K + 63) // 64
@@ -253,7 +274,7 @@ def box_nms_matrix(boxes, scores=None, iou_threshold: float = 0.5):
 
 
 def batch_erode(masks_u8: torch.Tensor, kernel_size: int = 9, num_round: int = 3) -> torch.Tensor:
-    m = masks_u8.contiguous()
+    m = _on(masks_u8.contiguous())
     B, H, W = m.shape
     out = torch.empty_like(m)
     _call("unmore_batch_erode", m.data_ptr(), B, H, W, int(kernel_size), int(num_round), out.data_ptr(), _stream())
@@ -262,7 +283,7 @@ def batch_erode(masks_u8: torch.Tensor, kernel_size: int = 9, num_round: int = 3
 
 def connected_components(masks_u8: torch.Tensor):
     """[B,128,128] u8 -> (counts [B] int32, boxes [B, CC_CAP, 4] int32 slice bounds) in scipy label order."""
-    m = masks_u8.contiguous()
+    m = _on(masks_u8.contiguous())
     B, H, W = m.shape
     cap = _lib.load().unmore_cc_cap()
     counts = torch.zeros((B,), dtype=torch.int32, device=m.device)
@@ -272,7 +293,7 @@ def connected_components(masks_u8: torch.Tensor):
 
 
 def anti_center_map(vote_maps: torch.Tensor, kernel_size: int = 5) -> torch.Tensor:
-    v = vote_maps.contiguous().to(torch.float32)
+    v = _on(vote_maps.contiguous().to(torch.float32))
     B, _, H, W = v.shape
     out = torch.empty((B, H, W), dtype=torch.float64, device=v.device)
     _call("unmore_anti_center_map", v.data_ptr(), B, H, W, int(kernel_size), out.data_ptr(), _stream())
@@ -299,7 +320,7 @@ def score_and_rasterise(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANN
 
 def mask_resize(masks_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     """[B,128,128] u8 -> [B,out_h,out_w] u8: bilinear + round-half-even like the reference's Resize on int masks."""
-    m = masks_u8.contiguous()
+    m = _on(masks_u8.contiguous())
     B, H, W = m.shape
     out = torch.zeros((B, out_h, out_w), dtype=torch.uint8, device=m.device)
     if B and out_h and out_w:
@@ -312,7 +333,7 @@ def final_scores(scores, tight, areas, keep, keep_counts, existence_score_thres=
     """-> out [n_img,cap,5] fp64 (score, existence, center, boundary, area_score), bbox xywh [n_img,cap,4],
     selected [n_img,cap] uint8 — all in NMS keep order."""
     n_img, cap = areas.shape
-    dev = areas.device
+    dev = _on(areas).device
     out = torch.zeros((n_img, cap, 5), dtype=torch.float64, device=dev)
     bbox = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
     sel = torch.zeros((n_img, cap), dtype=torch.uint8, device=dev)
@@ -327,7 +348,7 @@ def sat_build(planes: torch.Tensor) -> torch.Tensor:
     """[..., H, W] fp32 CUDA -> [..., H+1, W+1] fp64 exclusive 2-D prefix sums."""
     if not planes.is_cuda or planes.dtype != torch.float32:
         raise _lib.UnmoreError("sat_build needs a CUDA fp32 tensor")
-    p = planes.contiguous()
+    p = _on(planes.contiguous())
     H, W = p.shape[-2], p.shape[-1]
     n = p.numel() // (H * W) if H * W else 0
     out = torch.empty(p.shape[:-2] + (H + 1, W + 1), dtype=torch.float64, device=p.device)
@@ -350,7 +371,7 @@ def sat_build_fields(fields: torch.Tensor, channels, out: Optional[torch.Tensor]
 
 def box_sums(sat: torch.Tensor, plane: int, boxes: torch.Tensor, counts=None):
     """sat [n_img, P, H+1, W+1] fp64, boxes [n_img, cap, 4] -> (sums, means) [n_img, cap] fp64."""
-    n_img, P, H1, W1 = sat.shape
+    n_img, P, H1, W1 = _on(sat).shape
     cap, f64 = _check_boxes(boxes, n_img)
     sums = torch.zeros((n_img, cap), dtype=torch.float64, device=sat.device)
     means = torch.zeros((n_img, cap), dtype=torch.float64, device=sat.device)
@@ -367,7 +388,7 @@ def mask_pack(dense_u8: torch.Tensor) -> torch.Tensor:
         d = d.view(torch.uint8)
     if not d.is_cuda or d.dtype != torch.uint8:
         raise _lib.UnmoreError("mask_pack needs a CUDA uint8/bool tensor")
-    d = d.contiguous()
+    d = _on(d.contiguous())
     K, H, W = d.shape
     out = torch.empty((K, H, (W + 31) // 32), dtype=torch.int32, device=d.device)
     _call("unmore_mask_pack", d.data_ptr(), K, H, W, out.data_ptr(), _stream())
@@ -375,7 +396,7 @@ def mask_pack(dense_u8: torch.Tensor) -> torch.Tensor:
 
 
 def mask_stats(packed: torch.Tensor, W: int):
-    K, H, _ = packed.shape
+    K, H, _ = _on(packed).shape
     areas = torch.zeros((K,), dtype=torch.int32, device=packed.device)
     tight = torch.zeros((K, 4), dtype=torch.int32, device=packed.device)
     _call("unmore_mask_stats", packed.data_ptr(), K, H, W, areas.data_ptr(), tight.data_ptr(), _stream())
@@ -388,6 +409,7 @@ def mask_nms(packed: torch.Tensor, W: int, scores: torch.Tensor, iou_threshold: 
     K, H, _ = packed.shape
     dev = packed.device
     areas, tight = stats if stats is not None else mask_stats(packed, W)
+    _on(packed)
     nblk = (K + 63) // 64
     order = torch.empty((max(K, 1),), dtype=torch.int32, device=dev)
     matrix = torch.empty((max(K * nblk, 1),), dtype=torch.int64, device=dev)
@@ -402,7 +424,7 @@ def mask_nms(packed: torch.Tensor, W: int, scores: torch.Tensor, iou_threshold: 
 def mask_rle_counts(packed: torch.Tensor, W: int, max_runs: int = 4096):
     """Packed masks [K, H, ceil(W/32)] -> (counts [K, max_runs] int32 (as uint32), n_runs [K] int32):
     COCO column-major run lengths; rows with n_runs > max_runs are not filled."""
-    packed = packed.contiguous()
+    packed = _on(packed.contiguous())
     K, H, _ = packed.shape
     counts = torch.zeros((K, max_runs), dtype=torch.int32, device=packed.device)
     n_runs = torch.zeros((K,), dtype=torch.int32, device=packed.device)
@@ -410,3 +432,25 @@ def mask_rle_counts(packed: torch.Tensor, W: int, max_runs: int = 4096):
         _call("unmore_mask_rle_counts", packed.data_ptr(), K, H, W, int(max_runs), counts.data_ptr(), n_runs.data_ptr(),
               _stream())
     return counts, n_runs
+
+
+def detection_rows(max_rows: int, device) -> torch.Tensor:
+    """Zeroed row buffer [max_rows + 1, 6] fp64 for ``pack_detections`` (row 0 is the header / append cursor)."""
+    return torch.zeros((max_rows + 1, 6), dtype=torch.float64, device=device)
+
+
+def pack_detections(image_ids: torch.Tensor, bbox: torch.Tensor, out5: torch.Tensor, keep_counts: torch.Tensor,
+                    rows: torch.Tensor) -> torch.Tensor:
+    """Appends (image_id, x, y, w, h, score) rows of a scored batch to ``rows`` (see ``detection_rows``) on the
+    device, image-major in NMS keep order; no host round trip.  image_ids [B] int64, bbox [B,cap,4] fp32,
+    out5 [B,cap,5] fp64, keep_counts [B] int32."""
+    B, cap = bbox.shape[0], bbox.shape[1]
+    if image_ids.dtype != torch.int64 or image_ids.numel() != B or not bbox.is_contiguous() or not out5.is_contiguous():
+        raise _lib.UnmoreError("pack_detections: image_ids must be int64 [B]; bbox / out5 contiguous")
+    if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[1] != 6 or not rows.is_contiguous():
+        raise _lib.UnmoreError("pack_detections: rows must be contiguous fp64 [max_rows + 1, 6]")
+    _on(bbox)
+    if B and cap:
+        _call("unmore_pack_detections", image_ids.data_ptr(), bbox.data_ptr(), out5.data_ptr(), keep_counts.data_ptr(), cap, B,
+              rows.data_ptr(), rows.shape[0] - 1, _stream())
+    return rows
