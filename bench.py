@@ -518,6 +518,7 @@ def main():
             e2e_step()
         barrier()
         dt = (time.perf_counter() - t0) / reps
+        d2h_full, n_rle_full = d2h, n_rle
         e2e_step(with_rle=False)
         barrier()
         t0 = time.perf_counter()
@@ -529,11 +530,11 @@ def main():
             t = torch.tensor([dt, dt_rows], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt, dt_rows = float(t[0].item()), float(t[1].item())
-        e2e = {"value": n_global / dt, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": n_global / dt, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
                "host_pool_images": pool, "ms_per_step": dt * 1e3,
                "result": "detection rows (image_id, x, y, w, h, score) fp64 + COCO RLE run lengths of every kept mask "
                          f"(unmore_mask_rle_counts, {MAX_RUNS} int32 per mask + its length)",
-               "masks_rle_per_step": n_rle,
+               "masks_rle_per_step": n_rle_full,
                "rows_only": {"value": n_global / dt_rows, "ms_per_step": dt_rows * 1e3, "d2h_bytes_per_step": d2h_rows}}
         del h_fields, bufs
 

@@ -59,6 +59,18 @@ int unmore_crop_resize(const float* fields, int n_img, int C, int H, int W,
                        const int* channels_host, int n_channels, const void* boxes, int boxes_f64,
                        const int* counts, int cap, float* out, unmore_stream_t stream);
 
+/* The same two stand-alone resize ops in the SECOND resize mode, antialias=True (ATen _upsample_bilinear2d_aa):
+ * what torchvision >= 0.17 makes of the reference's transforms.Resize calls (object_reasoning.py:319,407,505;
+ * object_scoring.py:131,206,222) when the pinned 0.14.1 is not what is installed.  Bit-exact against torch 2.11
+ * CPU (weights with ATen's float/double mix, horizontal pass first, its accumulation order).  The fused
+ * kernels above implement antialias=False only; these produce the tiles for unmore_update_bbox_from_tiles and
+ * for inspection.  `scratch`: n_img*cap*n_channels*H*128 floats (crop) / B*128*out_w floats (mask). */
+int unmore_crop_resize_aa(const float* fields, int n_img, int C, int H, int W, const int* channels_host,
+                          int n_channels, const void* boxes, int boxes_f64, const int* counts, int cap,
+                          float* out, void* scratch, size_t scratch_bytes, unmore_stream_t stream);
+int unmore_mask_resize_aa(const unsigned char* masks, int B, int H, int W, int out_h, int out_w,
+                          unsigned char* out, void* scratch, size_t scratch_bytes, unmore_stream_t stream);
+
 /* center_reasoning — object_reasoning.py:525-580 with batch_erode (utils/misc.py:10-20) and
  * center_field_to_anti_center_map (object_reasoning.py:360-377) fused.
  * max_values_out [n_img, cap] fp64: amax of the masked anti-center map;

@@ -111,6 +111,48 @@ def gen_units(od):
     print("units.npz written")
 
 
+def gen_units_aa(od):
+    """Second resize mode (torchvision default antialias=True; run with UNMORE_REF_ANTIALIAS=1): the reference's own
+    Resize call pattern on crops and on int masks, its get_prediction_with_proposals tiles, and one round of
+    optimize_one_image_single_round on them."""
+    import math
+    import torchvision
+    from torchvision import transforms
+    assert os.environ.get("UNMORE_REF_ANTIALIAS") == "1", "run as: UNMORE_REF_ANTIALIAS=1 python -m oracle.gen_golden units_aa"
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    img = synth.make_fields(3)
+    boxes = np.array([[0, 0, 32, 32], [10.3, 20.7, 200.2, 300.9], [0, 0, 640, 480], [600.5, 400.25, 640, 480],
+                      [123.0, 45.0, 131.0, 52.0], [5.5, 5.5, 517.5, 261.5], [300.1, 100.9, 364.1, 228.9],
+                      [100.0, 50.0, 357.0, 179.0], [17.2, 300.4, 500.9, 460.0]])
+    crops = []
+    for b in boxes:
+        x1, y1, x2, y2 = int(math.floor(b[0])), int(math.floor(b[1])), int(math.ceil(b[2])), int(math.ceil(b[3]))
+        resize = transforms.Resize((128, 128), interpolation=torchvision.transforms.InterpolationMode.BILINEAR)
+        crops.append(resize(img[:, y1:y2, x1:x2]))
+    out["crop_boxes"] = boxes
+    out["crop_out"] = torch.stack(crops).numpy()
+    sdf, cen = _quiet(od.get_prediction_with_proposals, torch.tensor(boxes), img)
+    out["pred_sdf"] = sdf.cpu().numpy()
+    out["pred_center"] = cen.cpu().numpy()
+    d = od.update_bbox_with_boundary_fields(sdf.cpu())
+    out["a10_deltas"] = torch.stack(d, dim=1).numpy()
+    r = _quiet(od.optimize_one_image_single_round, img, torch.tensor(boxes), torch.zeros(len(boxes)))
+    out["round_boxes"] = r["updated_bboxes"].cpu().numpy()
+    out["round_labels"] = r["labels"].cpu().numpy()
+    masks = (torch.rand(3, 128, 128, generator=g) > 0.5).long()
+    yy, xx = torch.meshgrid(torch.arange(128), torch.arange(128), indexing="ij")
+    masks[1] = (((yy - 60) ** 2 + (xx - 70) ** 2) < 45 ** 2).long()
+    sizes = [(64, 64), (256, 256), (32, 32), (100, 300), (480, 640), (13, 17), (127, 129), (61, 67), (1, 1), (3, 200)]
+    out["n2_masks"] = masks.numpy().astype(np.uint8)
+    out["n2_sizes"] = np.array(sizes)
+    for k, (h, w) in enumerate(sizes):
+        rs = transforms.Resize((h, w), interpolation=torchvision.transforms.InterpolationMode.BILINEAR)
+        out[f"n2_out_{k}"] = np.stack([rs(masks[i].unsqueeze(0))[0].numpy() for i in range(3)]).astype(np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "units_aa.npz"), **out)
+    print("units_aa.npz written")
+
+
 def gen_scene(od, index, n_prop, tag, n_round=50):
     """Stage-by-stage vectors of main_object_discovery's body on one synthetic image."""
     H, W = 480, 640
@@ -326,6 +368,8 @@ def main():
     which = sys.argv[1:] or ["units", "scene_a", "scene_b", "main", "scene_cc"]
     if "units" in which:
         gen_units(od)
+    if "units_aa" in which:
+        gen_units_aa(od)
     if "scene_a" in which:
         gen_scene(od, index=0, n_prop=512, tag="a")          # BASELINE.json configs[0]
     if "scene_b" in which:

@@ -132,6 +132,77 @@ def resize_bilinear_np(v: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     return _fma32(p11, v11, _fma32(p10, v10, _fma32(p00, v00, p01 * v01)))
 
 
+# ---- antialias=True: ATen's _upsample_bilinear2d_aa, the mode torchvision >= 0.17 gives transforms.Resize by
+# default (SURVEY.md section 8c hazard 1; the reference pins torchvision 0.14.1 where tensors are never
+# antialiased, so antialias=False is the primary mode of this repo and this is the second one).
+# PINNED against torch 2.11 CPU in the build container: tests/test_oracle_golden.py::test_antialias_resize_bit_exact.
+def aa_index_weights(in_size: int, out_size: int):
+    """HelperInterpBase::_compute_indices_min_size_weights_aa (UpSampleKernel.cpp) with its float / double mix
+    (opmath = float; literals 0.5 / 1.0 are double): per output index -> (xmin, fp32 weights[xsize]).
+
+        scale = float(in) / float(out);  support = scale >= 1 ? scale : 1;  invscale = scale >= 1 ? float(1.0 / scale) : 1
+        center = float(double(scale) * (i + 0.5))
+        xmin = max(int64(double(float(center - support)) + 0.5), 0);  xmax = min(int64(double(float(center + support)) + 0.5), in)
+        w_j = tri(float((double(float(float(j + xmin) - center)) + 0.5) * double(invscale))),  tri(x) = float(1.0 - |x|) if |x| < 1 else 0
+        w_j /= sum_j w_j   (fp32 running sum, fp32 division)
+    """
+    f32 = np.float32
+    scale = f32(in_size) / f32(out_size)
+    support = scale if scale >= 1.0 else f32(1.0)
+    invscale = f32(1.0 / np.float64(scale)) if scale >= 1.0 else f32(1.0)
+    out = []
+    for i in range(out_size):
+        center = f32(np.float64(scale) * (i + 0.5))
+        xmin = max(int(np.float64(f32(center - support)) + 0.5), 0)
+        xmax = min(int(np.float64(f32(center + support)) + 0.5), in_size)
+        n = xmax - xmin
+        w = np.zeros(n, f32)
+        total = f32(0)
+        for j in range(n):
+            x = f32((np.float64(f32(f32(j + xmin) - center)) + 0.5) * np.float64(invscale))
+            x = -x if x < 0 else x
+            w[j] = f32(1.0 - np.float64(x)) if x < 1.0 else f32(0)
+            total = f32(total + w[j])
+        if total != 0:
+            w = (w / total).astype(f32)
+        out.append((xmin, w))
+    return out
+
+
+def _aa_pass(src: np.ndarray, taps) -> np.ndarray:
+    """One separable pass along the last axis: src [rows, in] -> [rows, out].  The accumulation order is the
+    compiled loop of interpolate_aa_single_dim in this torch build, found by experiment and pinned by the test:
+    t = s0 * w0 (rounded); the next 4 * floor((n - 1) / 4) taps are added with SEPARATE multiply and add (the
+    unrolled main loop), the remaining (n - 1) mod 4 taps with a fused multiply-add (the scalar remainder loop)."""
+    out = np.empty((src.shape[0], len(taps)), np.float32)
+    for i, (xmin, w) in enumerate(taps):
+        n = len(w)
+        t = (src[:, xmin] * w[0]).astype(np.float32)
+        main = ((n - 1) // 4) * 4
+        for j in range(1, 1 + main):
+            t = (t + (src[:, xmin + j] * w[j]).astype(np.float32)).astype(np.float32)
+        for j in range(1 + main, n):
+            t = _fma32(src[:, xmin + j], w[j], t)
+        out[:, i] = t
+    return out
+
+
+def resize_bilinear_aa_np(v: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """Bit-exact numpy restatement of F.interpolate(bilinear, align_corners=False, antialias=True) on one fp32
+    [H, W] plane (torch 2.11 CPU): the horizontal pass over every source row first, then the vertical pass."""
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    ih, iw = v.shape
+    t = _aa_pass(v, aa_index_weights(iw, out_w))                       # [ih, out_w]
+    return _aa_pass(np.ascontiguousarray(t.T), aa_index_weights(ih, out_h)).T.copy()
+
+
+def crop_resize_aa(image: torch.Tensor, box, size=(CROP, CROP)) -> torch.Tensor:
+    """crop_resize with torchvision's current default antialias=True (the real call, for pinning)."""
+    x1, y1, x2, y2 = snap_box(box)
+    crop = image[:, y1:y2, x1:x2]
+    return F.interpolate(crop.unsqueeze(0), size=list(size), mode="bilinear", align_corners=False, antialias=True)[0]
+
+
 def norm2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """torch.norm(stack(a, b), dim=1) restated: round(a*a) + round(b*b), then a CORRECTLY
     ROUNDED sqrt (the norm kernel calls std::sqrt).  torch.sqrt must not be used here: its

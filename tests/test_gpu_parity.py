@@ -776,3 +776,31 @@ def test_analyze_cc_more_components_than_the_device_buffer(dev):
     kb, kc = odc.discover_batch(f2, p2)
     assert_boxes_close(kb[0, : int(kc[0])].cpu().numpy(), O.discover_image(f, np.concatenate([props, props[:1]]), args), "batch[0]")
     assert_boxes_close(kb[1, : int(kc[1])].cpu().numpy(), O.discover_image(synth.make_fields(5), synth.make_proposals(5, 4), args), "batch[1]")
+
+
+def test_antialias_mode_unit_ops(golden_dir, dev, ops):
+    """Second resize mode (antialias=True, torchvision >= 0.17 default): the stand-alone a2 / N2 ops against
+    goldens produced by running the reference with that default (UNMORE_REF_ANTIALIAS=1 python -m
+    oracle.gen_golden units_aa): crops and get_prediction_with_proposals tiles bit-exact, mask resize bit-exact,
+    and a10 on those tiles within 1e-5."""
+    from unmore_b200.object_reasoning import Object_Discovery, default_args
+    g = _load(golden_dir, "units_aa.npz")
+    fields = synth.make_fields(3).to(dev)[None].contiguous()
+    boxes = torch.tensor(g["crop_boxes"], device=dev)[None].contiguous()
+    crops = ops.crop_resize(fields, boxes, [0, 1, 2, 3], antialias=True)[0]
+    assert np.array_equal(crops.cpu().numpy(), g["crop_out"])
+    plain = ops.crop_resize(fields, boxes, [0, 1, 2, 3])[0]
+    assert not torch.equal(plain, crops)                       # the modes differ on crops larger than the tile
+    oda = Object_Discovery(default_args(antialias=True), device=dev)
+    sdf, cen = oda.get_prediction_with_proposals(g["crop_boxes"], fields[0])
+    assert np.array_equal(sdf.cpu().numpy(), g["pred_sdf"]) and np.array_equal(cen.cpu().numpy(), g["pred_center"])
+    d, _ = ops.update_bbox_from_tiles(sdf.contiguous())
+    assert_rel(d.cpu().numpy(), g["a10_deltas"], "a10 on antialiased tiles")
+    masks = torch.tensor(g["n2_masks"], device=dev)
+    for k, (h, w) in enumerate(g["n2_sizes"]):
+        out = ops.mask_resize(masks, int(h), int(w), antialias=True)
+        assert np.array_equal(out.cpu().numpy(), g[f"n2_out_{k}"]), (h, w)
+    # ragged counts + proposal slicing of the scratch-bounded wrapper
+    cnt = torch.tensor([4], dtype=torch.int32, device=dev)
+    part = ops.crop_resize(fields, boxes, [0], counts=cnt, antialias=True)[0]
+    assert torch.equal(part[:4, 0], crops[:4, 0]) and float(part[4:].abs().max()) == 0.0

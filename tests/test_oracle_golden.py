@@ -202,3 +202,24 @@ def test_analyze_cc_discovery(golden_dir):
     idx, n_prop = int(g["disc_index"]), int(g["disc_n_prop"])
     det = O.discover_image(synth.make_fields(idx), synth.make_proposals(idx, n_prop), O.make_args(analyze_cc=True))
     assert np.array_equal(det.view(np.int32), g["disc"].view(np.int32))
+
+
+def test_antialias_resize_bit_exact():
+    """The second resize mode (torchvision >= 0.17 default antialias=True, SURVEY.md section 8c hazard 1): the
+    numpy restatement of ATen's _upsample_bilinear2d_aa — weights with their float/double mix, horizontal pass
+    first, and the compiled accumulation order (4-tap unrolled mul+add groups, fused remainder) — is bit-identical
+    to torch on down-, up- and mixed sampling, on windows up to 1024 px, and through the int-mask path
+    (Resize of an int64 mask = float resize + round half to even, object_scoring.py:206-207)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    for ih, iw, oh, ow in [(480, 640, 128, 128), (300, 200, 128, 128), (129, 257, 128, 128), (37, 500, 128, 128),
+                           (64, 640, 128, 128), (1024, 1024, 128, 128), (100, 50, 128, 128), (13, 7, 128, 128),
+                           (128, 128, 37, 61), (128, 128, 5, 9), (128, 128, 200, 100), (128, 128, 128, 64), (1, 1, 128, 128)]:
+        x = torch.randn((1, 1, ih, iw), generator=g)
+        ref = F.interpolate(x, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)[0, 0].numpy()
+        assert np.array_equal(O.resize_bilinear_aa_np(x[0, 0].numpy(), oh, ow), ref), (ih, iw, oh, ow)
+    m = (torch.rand((128, 128), generator=g) > 0.5).to(torch.int64)
+    for oh, ow in [(37, 61), (200, 100), (64, 64), (5, 300), (128, 128)]:
+        f = F.interpolate(m[None, None].float(), size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)[0, 0]
+        got = np.round(O.resize_bilinear_aa_np(m.numpy().astype(np.float32), oh, ow))
+        assert np.array_equal(got, torch.round(f).numpy()), (oh, ow)

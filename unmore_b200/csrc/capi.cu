@@ -114,6 +114,33 @@ int unmore_crop_resize(const float* fields, int n_img, int C, int H, int W, cons
                    "crop_resize_kernel");
 }
 
+int unmore_crop_resize_aa(const float* fields, int n_img, int C, int H, int W, const int* channels_host, int n_channels,
+                          const void* boxes, int boxes_f64, const int* counts, int cap, float* out, void* scratch,
+                          size_t scratch_bytes, unmore_stream_t stream) {
+  if (int e = check_fields(fields, n_img, C, H, W)) return e;
+  if (!boxes || !out || !channels_host || cap < 0 || n_channels < 1 || n_channels > 4)
+    return fail(UNMORE_E_INVALID, "unmore_crop_resize_aa: bad argument (1..4 channels)");
+  for (int i = 0; i < n_channels; ++i)
+    if (channels_host[i] < 0 || channels_host[i] >= C) return fail(UNMORE_E_INVALID, "unmore_crop_resize_aa: channel out of range");
+  const size_t need = (size_t)n_img * cap * n_channels * H * 128 * sizeof(float);
+  if (need && (!scratch || scratch_bytes < need))
+    return fail(UNMORE_E_CAPACITY, "unmore_crop_resize_aa: scratch must hold n_img*cap*n_channels*H*128 floats (%zu bytes)", need);
+  return cuda_fail(launch_crop_resize_aa(fields, n_img, C, H, W, channels_host, n_channels, boxes, boxes_f64, counts, cap, out,
+                                         reinterpret_cast<float*>(scratch), (cudaStream_t)stream),
+                   "crop_resize_aa kernels");
+}
+
+int unmore_mask_resize_aa(const unsigned char* masks, int B, int H, int W, int out_h, int out_w, unsigned char* out,
+                          void* scratch, size_t scratch_bytes, unmore_stream_t stream) {
+  if (B < 0 || out_h < 0 || out_w < 0 || (B > 0 && (!masks || !out))) return fail(UNMORE_E_INVALID, "unmore_mask_resize_aa: bad argument");
+  if (H != 128 || W != 128) return fail(UNMORE_E_INVALID, "unmore_mask_resize_aa: masks must be 128x128 (the crop side of the reference)");
+  const size_t need = (size_t)B * 128 * out_w * sizeof(float);
+  if (need && (!scratch || scratch_bytes < need))
+    return fail(UNMORE_E_CAPACITY, "unmore_mask_resize_aa: scratch must hold B*128*out_w floats (%zu bytes)", need);
+  return cuda_fail(launch_mask_resize_aa(masks, B, out_h, out_w, out, reinterpret_cast<float*>(scratch), (cudaStream_t)stream),
+                   "mask_resize_aa kernels");
+}
+
 int unmore_center_reasoning(const float* fields, int n_img, int C, int H, int W, int ch_sdf, int ch_center_row,
                             int ch_center_col, const void* boxes, int boxes_f64, const int* counts, int cap,
                             double center_score_max_thres, double* max_values_out, int* argmax_out,
@@ -319,7 +346,7 @@ int unmore_box_sums(const double* sat, int n_img, int planes_per_img, int plane,
 
 int unmore_mask_pack(const unsigned char* in, size_t K, int H, int W, uint32_t* out, unmore_stream_t stream) {
   if (H <= 0 || W <= 0 || (K > 0 && (!in || !out))) return fail(UNMORE_E_INVALID, "unmore_mask_pack: bad argument");
-  return cuda_fail(launch_mask_pack(in, out, K, H, W, (cudaStream_t)stream), "pack_kernel");
+  return cuda_fail(launch_mask_pack(in, out, K, H, W, num_sms(), (cudaStream_t)stream), "pack_kernel");
 }
 
 int unmore_mask_stats(const uint32_t* masks, int K, int H, int W, int* areas_out, int* tight_out,

@@ -108,6 +108,29 @@ __device__ __forceinline__ void st_shared_b64_if(bool pred, unsigned addr, unsig
   asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.b64 [%1+%3], %2; }" ::"r"((unsigned)pred), "r"(addr), "l"(v), "n"(OFF) : "memory");
 }
 
+// ---- bulk-copy engine (TMA, cp.async.bulk) + mbarrier primitives, shared by the SAT scan and the TMA-fed
+// existence kernel: one elected lane issues whole-row copies into shared memory, completion is tracked by the
+// transaction count of an mbarrier, consumers spin on its phase parity.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+
 // a predicate that is the same in every lane, stated in a form the compiler can see (vote result)
 __device__ __forceinline__ bool warp_uniform(bool b) { return __any_sync(kFullMask, b) != 0; }
 

@@ -12,30 +12,49 @@
 namespace unmore {
 
 // ---- pack --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t nz4(uint32_t w) {  // 4 bytes -> 4 bits (byte != 0)
-  const uint32_t m = __vcmpne4(w, 0u);                 // 0xFF per non-zero byte
-  return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+// 4 bytes -> 4 bits (byte != 0), 5 instructions: bit 7 of every byte := "byte is non-zero" (mask the top bits so the
+// add cannot carry across bytes, add 0x7f, OR the original top bit back in), then one multiply gathers bits
+// 7 / 15 / 23 / 31 into bits 28..31 (0x00204081 = 2^21 + 2^14 + 2^7 + 1; the ten partial-product bits land on distinct
+// positions, so nothing carries).  The SIMD-video form (__vcmpne4 + four shift/mask pairs) is emulated on sm_100a and
+// cost ~18 ALU instructions per word: the kernel sat on the ALU pipe (91%) at 0.66-0.81 of HBM (profiles/r01_pack_kernel.md);
+// the multiply runs on the otherwise idle FMA pipe.
+__device__ __forceinline__ uint32_t nz4(uint32_t w) {
+  const uint32_t m = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+  uint32_t g;
+  asm("mul.lo.u32 %0, %1, 0x00204081;" : "=r"(g) : "r"(m));
+  return g >> 28;
 }
 
-// fast path: W % 32 == 0.  A lane loads 16 pixels (one uint4), pairs of lanes form a word; each
-// thread keeps four independent 16-byte loads in flight (grid-stride unrolled) to cover HBM latency.
+// fast path: W % 32 == 0.  A lane loads 16 pixels (one uint4), pairs of lanes form a word.  Persistent grid-stride loop:
+// every thread keeps kPackUnroll independent 16-byte loads in flight and requests the NEXT batch before it packs the
+// current one, so the HBM pipe never drains between batches and there is no per-CTA launch / drain overhead (the
+// one-shot form reached 0.57 / 0.74 / 0.80 of the measured copy bandwidth at 1k / 4k / 16k masks).
 constexpr int kPackUnroll = 4;
 __global__ void __launch_bounds__(256) pack_kernel_vec(const uint4* __restrict__ in, uint32_t* __restrict__ out,
                                                        size_t n_vec) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint4 v[kPackUnroll];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;   // even: lane pairs stay together in every batch
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 v[kPackUnroll], nxt[kPackUnroll];
 #pragma unroll
   for (int u = 0; u < kPackUnroll; ++u) {
     const size_t i = i0 + u * stride;
     v[u] = i < n_vec ? __ldcs(in + i) : make_uint4(0u, 0u, 0u, 0u);
   }
+  for (; i0 < n_vec; i0 += kPackUnroll * stride) {
+    const size_t j0 = i0 + kPackUnroll * stride;
 #pragma unroll
-  for (int u = 0; u < kPackUnroll; ++u) {
-    const size_t i = i0 + u * stride;
-    const uint32_t bits = nz4(v[u].x) | (nz4(v[u].y) << 4) | (nz4(v[u].z) << 8) | (nz4(v[u].w) << 12);
-    const uint32_t hi = __shfl_down_sync(kFullMask, bits, 1);
-    if (!(threadIdx.x & 1) && i < n_vec) __stcs(out + (i >> 1), bits | (hi << 16));
+    for (int u = 0; u < kPackUnroll; ++u) {
+      const size_t i = j0 + u * stride;
+      nxt[u] = i < n_vec ? __ldcs(in + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kPackUnroll; ++u) {
+      const size_t i = i0 + u * stride;
+      const uint32_t bits = nz4(v[u].x) | (nz4(v[u].y) << 4) | (nz4(v[u].z) << 8) | (nz4(v[u].w) << 12);
+      const uint32_t hi = __shfl_down_sync(kFullMask, bits, 1);
+      if (!(threadIdx.x & 1) && i < n_vec) __stcs(out + (i >> 1), bits | (hi << 16));
+      v[u] = nxt[u];
+    }
   }
 }
 
@@ -52,13 +71,15 @@ __global__ void __launch_bounds__(256) pack_kernel_generic(const unsigned char* 
   out[q] = word;
 }
 
-int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, cudaStream_t stream) {
+int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, int num_sms, cudaStream_t stream) {
   if (n_masks == 0) return 0;
   const int Wp = (W + 31) >> 5;
   if ((W & 31) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
     const size_t n_vec = n_masks * H * (size_t)W / 16;
     const size_t per_block = 256 * (size_t)kPackUnroll;   // n_vec is even (W % 32 == 0), so lane pairs never straddle strides
-    pack_kernel_vec<<<(unsigned)((n_vec + per_block - 1) / per_block), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), out, n_vec);
+    const size_t want = (n_vec + per_block - 1) / per_block;
+    const size_t resident = (size_t)num_sms * 8;           // 8 CTAs of 256 threads fill an SM
+    pack_kernel_vec<<<(unsigned)(want < resident ? want : resident), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), out, n_vec);
   } else {
     const size_t total = n_masks * H * (size_t)Wp;
     pack_kernel_generic<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, n_masks * (size_t)H, W, Wp);

@@ -49,6 +49,11 @@ int launch_existence(const ExistParams& p, int num_sms, cudaStream_t stream);
 int launch_crop_resize(const float* fields, int n_img, int C, int H, int W, const int* channels, int n_ch,
                        const void* boxes, int boxes_f64, const int* counts, int cap, float* out, cudaStream_t stream);
 
+int launch_crop_resize_aa(const float* fields, int n_img, int C, int H, int W, const int* channels, int n_ch,
+                          const void* boxes, int boxes_f64, const int* counts, int cap, float* out, float* scratch,
+                          cudaStream_t stream);
+int launch_mask_resize_aa(const unsigned char* masks, int B, int oh, int ow, unsigned char* out, float* scratch, cudaStream_t stream);
+
 // ---- center.cu -----------------------------------------------------------------------
 #ifndef UNMORE_CC_CAP
 #define UNMORE_CC_CAP 16   // connected-component boxes kept per proposal (--analyze_cc); overflow is counted
@@ -158,7 +163,7 @@ int launch_box_sums(const double* sat, int planes_per_img, int plane, int H, int
                     const int* counts, int cap, int n_img, double* sums, double* means, cudaStream_t stream);
 
 // ---- masks.cu ------------------------------------------------------------------------
-int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, cudaStream_t stream);
+int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int H, int W, int num_sms, cudaStream_t stream);
 int launch_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs, uint32_t* counts, int* n_runs,
                       cudaStream_t stream);
 int launch_mask_stats(const uint32_t* masks, int K, int H, int Wp, int* areas, int4* tight, cudaStream_t stream);

@@ -85,6 +85,10 @@ class Object_Discovery:
         self.width = None
         self.test_dataset = test_dataset
         self.result_folder = result_folder
+        # resize mode of the STAND-ALONE tile ops (get_prediction_with_proposals): False = torchvision 0.14.1
+        # semantics (what the reference pins and the fused kernels implement), True = ATen's antialiased kernel
+        # (torchvision >= 0.17's default).  args.antialias, when present, sets it.
+        self.antialias = bool(getattr(self.args, "antialias", False))
 
     # ---- a1 ---------------------------------------------------------------------------
     @staticmethod
@@ -147,7 +151,7 @@ class Object_Discovery:
         boundary-distance and center fields, (sdf_maps [N,128,128], center_fields [N,2,128,128])."""
         boxes = self._boxes(proposals)
         ch = self.channels
-        crops = ops.crop_resize(self._fields(image), boxes, [ch.sdf, ch.center_row, ch.center_col])[0]
+        crops = ops.crop_resize(self._fields(image), boxes, [ch.sdf, ch.center_row, ch.center_col], antialias=self.antialias)[0]
         return crops[:, 0], crops[:, 1:3]
 
     # ---- a7 ---------------------------------------------------------------------------
@@ -320,7 +324,7 @@ class Object_Discovery:
         NMS for a batch of images, entirely on device.
 
         fields [B,4,H,W] fp32, proposals [B,N,4] fp64/fp32, counts [B] int32 or None.
-        Returns (boxes [B, 5N (9N with --analyze_cc), 4] fp32, counts [B] int32) in the reference's output order."""
+        Returns (boxes [B, 5N (9N + 256 with --analyze_cc), 4] fp32, counts [B] int32) in the reference's output order."""
         a = self.args
         ch = self.channels
         B, N = proposals.shape[0], proposals.shape[1]
@@ -334,7 +338,9 @@ class Object_Discovery:
         cc_on = bool(getattr(a, "analyze_cc", False))
         _, am1, sp1, cc = ops.center_reasoning(fields, p1, c1, thr=a.center_score_max_thres, ch=ch, ws=ws,
                                                analyze_cc=cc_on)
-        split_cap = 8 * N if cc_on else 4 * N   # 4 split boxes per failing proposal (+ component boxes with --analyze_cc)
+        # 4 split boxes per failing proposal; with --analyze_cc the component boxes of passing proposals follow
+        # (a speckled mask can carry dozens: the reference has no limit, here the list holds 4N + 4N + 256 rows)
+        split_cap = 8 * N + 256 if cc_on else 4 * N
         cap_out = N + split_cap
         refine_in = torch.zeros((B, cap_out, 4), dtype=f64, device=dev)
         rc = torch.zeros((B,), dtype=torch.int32, device=dev)

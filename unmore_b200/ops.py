@@ -74,7 +74,7 @@ _timer: Optional[StageTimer] = None
 LAUNCHES = 0  # kernels launched through the C ABI since import (gpu_launches in bench.py)
 
 # kernels per C-ABI call (memsets not counted); +1 when a counts prefix is built
-_KERNELS = {"unmore_crop_resize": 1, "unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
+_KERNELS = {"unmore_crop_resize": 1, "unmore_crop_resize_aa": 2, "unmore_mask_resize_aa": 2, "unmore_existence_scores": 1, "unmore_center_reasoning": 1, "unmore_boundary_refine": 1,
             "unmore_update_bbox_from_tiles": 1, "unmore_compact_boxes": 1, "unmore_box_nms": 1,
             "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_connected_components": 1, "unmore_box_nms_matrix": 3,
             "unmore_score_and_rasterise": 1, "unmore_mask_resize": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
@@ -146,14 +146,30 @@ def existence_scores(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANNELS
     return out
 
 
-def crop_resize(fields, boxes, channels, counts=None):
-    """Resized crops [n_img, cap, len(channels), 128, 128] fp32 (a2 / a4 as a stand-alone op)."""
+def crop_resize(fields, boxes, channels, counts=None, antialias: bool = False):
+    """Resized crops [n_img, cap, len(channels), 128, 128] fp32 (a2 / a4 as a stand-alone op).
+    ``antialias=True`` is the second resize mode (torchvision >= 0.17's default for transforms.Resize)."""
     import ctypes
     n_img, C, H, W = _check_fields(fields)
     cap, f64 = _check_boxes(boxes, n_img)
     _check_counts(counts, n_img)
     ch = (ctypes.c_int * len(channels))(*[int(c) for c in channels])
     out = torch.zeros((n_img, cap, len(channels), CROP, CROP), dtype=torch.float32, device=fields.device)
+    if cap and antialias:
+        # the intermediate of the separable pass lives in scratch: bound it by walking the proposals in slices
+        per_box = len(channels) * H * CROP * 4
+        step = max(1, min(cap, (256 << 20) // max(1, per_box * n_img)))
+        for c0 in range(0, cap, step):
+            c1 = min(cap, c0 + step)
+            bsl = boxes[:, c0:c1].contiguous()
+            osl = torch.zeros((n_img, c1 - c0, len(channels), CROP, CROP), dtype=torch.float32, device=fields.device)
+            cnt = None if counts is None else (counts - c0).clamp(0, c1 - c0).to(torch.int32)
+            scratch = torch.empty((n_img * (c1 - c0) * per_box // 4,), dtype=torch.float32, device=fields.device)
+            _on(fields)
+            _call("unmore_crop_resize_aa", fields.data_ptr(), n_img, C, H, W, ctypes.cast(ch, ctypes.c_void_p), len(channels),
+                  bsl.data_ptr(), f64, _ptr(cnt), c1 - c0, osl.data_ptr(), scratch.data_ptr(), scratch.numel() * 4, _stream())
+            out[:, c0:c1] = osl
+        return out
     if cap:
         _call("unmore_crop_resize", fields.data_ptr(), n_img, C, H, W, ctypes.cast(ch, ctypes.c_void_p), len(channels),
               boxes.data_ptr(), f64, _ptr(counts), cap, out.data_ptr(), _stream())
@@ -318,11 +334,17 @@ def score_and_rasterise(fields, boxes, counts=None, ch: Channels = DEFAULT_CHANN
     return scores, tight, areas, masks
 
 
-def mask_resize(masks_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
-    """[B,128,128] u8 -> [B,out_h,out_w] u8: bilinear + round-half-even like the reference's Resize on int masks."""
+def mask_resize(masks_u8: torch.Tensor, out_h: int, out_w: int, antialias: bool = False) -> torch.Tensor:
+    """[B,128,128] u8 -> [B,out_h,out_w] u8: bilinear + round-half-even like the reference's Resize on int masks
+    (``antialias=True``: the second resize mode)."""
     m = _on(masks_u8.contiguous())
     B, H, W = m.shape
     out = torch.zeros((B, out_h, out_w), dtype=torch.uint8, device=m.device)
+    if B and out_h and out_w and antialias:
+        scratch = torch.empty((B * CROP * out_w,), dtype=torch.float32, device=m.device)
+        _call("unmore_mask_resize_aa", m.data_ptr(), B, H, W, int(out_h), int(out_w), out.data_ptr(), scratch.data_ptr(),
+              scratch.numel() * 4, _stream())
+        return out
     if B and out_h and out_w:
         _call("unmore_mask_resize", m.data_ptr(), B, H, W, int(out_h), int(out_w), out.data_ptr(), _stream())
     return out
