@@ -71,6 +71,32 @@ int unmore_crop_resize_aa(const float* fields, int n_img, int C, int H, int W, c
 int unmore_mask_resize_aa(const unsigned char* masks, int B, int H, int W, int out_h, int out_w,
                           unsigned char* out, void* scratch, size_t scratch_bytes, unmore_stream_t stream);
 
+/* The tile path of the second resize mode: the reasoning stages on PRE-RESAMPLED tiles (from unmore_crop_resize_aa,
+ * or from anywhere else — e.g. the real per-crop nets of the reference, object_reasoning.py:311-333), so that
+ * existence_checking, center_reasoning, one round of optimize_one_image_single_round and main_object_scoring run
+ * with torchvision's antialias=True semantics.  Same arithmetic as the fused kernels after the resample.
+ *   unmore_tile_means                      tiles [M] x [128,128] (tile_stride floats apart) -> mean per tile (a3)
+ *   unmore_center_reasoning_from_tiles     tiles [n_img*cap, 3, 128,128] = (sdf, center_row, center_col) (a5-a8)
+ *   unmore_boundary_round_from_tiles       tiles [M, 128,128] (sdf) + boxes [M,4] -> updated boxes fp32 / labels
+ *                                          (a10-a12 of ONE round; deltas_ws [M,4] and max_ws [M] are scratch)
+ *   unmore_score_and_rasterise_from_tiles  tiles [n_img*cap, 4, 128,128] = (sdf, center_row, center_col, existence);
+ *                                          the masks are resized back to the box with the antialiased kernel (a15) */
+int unmore_tile_means(const float* tiles, long long tile_stride, int M, float* means_out, unmore_stream_t stream);
+int unmore_center_reasoning_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes,
+                                       int boxes_f64, const int* counts, int cap,
+                                       double center_score_max_thres, double* max_values_out,
+                                       int* argmax_out, double* splits_out, unsigned char* cc_counts_out,
+                                       double* cc_boxes_out, int* cc_overflow, void* ws,
+                                       unmore_stream_t stream);
+int unmore_boundary_round_from_tiles(const float* tiles, int M, const void* boxes, int boxes_f64, int H, int W,
+                                     float max_sdf_thres, float max_shrink_threshold, float delta_ratio,
+                                     float* boxes_out, float* labels_out, float* deltas_ws, float* max_ws,
+                                     unmore_stream_t stream);
+int unmore_score_and_rasterise_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes,
+                                          int boxes_f64, const int* counts, int cap, float* scores_out,
+                                          float* tight_out, int* areas_out, uint32_t* masks_out,
+                                          unmore_stream_t stream);
+
 /* center_reasoning — object_reasoning.py:525-580 with batch_erode (utils/misc.py:10-20) and
  * center_field_to_anti_center_map (object_reasoning.py:360-377) fused.
  * max_values_out [n_img, cap] fp64: amax of the masked anti-center map;

@@ -374,6 +374,9 @@ def main():
         gen_scene(od, index=0, n_prop=512, tag="a")          # BASELINE.json configs[0]
     if "scene_b" in which:
         gen_scene(od, index=5, n_prop=160, tag="b", n_round=50)
+    if "scene_aa" in which:   # second resize mode: UNMORE_REF_ANTIALIAS=1 python -m oracle.gen_golden scene_aa
+        assert os.environ.get("UNMORE_REF_ANTIALIAS") == "1"
+        gen_scene(od, index=5, n_prop=160, tag="aa", n_round=50)
     if "main" in which:
         gen_main_loop(od)
     if "scene_cc" in which:

@@ -804,3 +804,67 @@ def test_antialias_mode_unit_ops(golden_dir, dev, ops):
     cnt = torch.tensor([4], dtype=torch.int32, device=dev)
     part = ops.crop_resize(fields, boxes, [0], counts=cnt, antialias=True)[0]
     assert torch.equal(part[:4, 0], crops[:4, 0]) and float(part[4:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# the whole parity suite of one scene in the SECOND resize mode (antialias=True, tile path) against goldens
+# produced by running the reference with torchvision's current default
+# (UNMORE_REF_ANTIALIAS=1 python -m oracle.gen_golden scene_aa)
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def oda(dev):
+    from unmore_b200.object_reasoning import Object_Discovery, default_args
+    return Object_Discovery(default_args(antialias=True), device=dev)
+
+
+def test_antialias_scene_existence_and_center(golden_dir, oda, dev):
+    g = _load(golden_dir, "scene_aa.npz")
+    idx, n_prop = int(g["index"]), int(g["n_prop"])
+    fields = synth.make_fields(idx).to(dev)
+    props = torch.tensor(synth.make_proposals(idx, n_prop))
+    ex = oda.existence_checking(fields, props)["existence_scores"]
+    assert_rel(ex.numpy(), g["existence_scores"], "existence (antialias)")
+    assert np.array_equal(ex.numpy() >= 0.1, g["existence_scores"] >= 0.1)
+    p1 = props[torch.tensor(g["existence_scores"]) >= 0.1]
+    cr = oda.center_reasoning(fields, p1)
+    assert np.array_equal(cr["proposals_pass_singularity"].cpu().numpy(), g["pass1"])
+    assert np.array_equal(cr["splited_new_proposals"].cpu().numpy().reshape(-1, 4), g["split"].reshape(-1, 4))
+    if len(g["split"]):
+        sp = torch.tensor(g["split"])
+        ex2 = oda.existence_checking(fields, sp)["existence_scores"].numpy()
+        assert_rel(ex2, g["split_existence"], "split existence (antialias)")
+        cr2 = oda.center_reasoning(fields, sp[torch.tensor(g["split_existence"]) >= 0.1])
+        assert np.array_equal(cr2["proposals_pass_singularity"].cpu().numpy(), g["pass2"])
+
+
+def test_antialias_scene_rounds_trajectory_discovery(golden_dir, oda, dev):
+    g = _load(golden_dir, "scene_aa.npz")
+    idx = int(g["index"])
+    fields = synth.make_fields(idx).to(dev)
+    for r in range(int(g["n_trace"])):                       # every recorded round, teacher-forced
+        out = oda.optimize_one_image_single_round(fields, torch.tensor(g[f"r{r}_in"]))
+        assert np.array_equal(out["labels"].cpu().numpy(), g[f"r{r}_labels"]), f"labels, round {r}"
+        assert_boxes_close(out["updated_bboxes"].cpu().numpy(), g[f"r{r}_out"], f"round {r} (antialias)")
+    br = oda.boundary_reasoning(fields, torch.tensor(g["refine_in"]))
+    assert np.array_equal(br["labels"].cpu().numpy(), g["final_labels"])
+    assert_boxes_close(br["proposals"].cpu().numpy(), g["final_proposals"], "final proposals (antialias)")
+    det = oda.discover_image(fields, synth.make_proposals(idx, int(g["n_prop"])))
+    assert_boxes_close(det, g["discovered"], "discovered (antialias)")
+    plain = _load(golden_dir, "scene_b.npz")                 # same scene in the primary mode: the modes really differ
+    assert plain["discovered"].shape != g["discovered"].shape or not np.allclose(plain["discovered"], g["discovered"], atol=1e-3)
+
+
+def test_antialias_scene_scoring(golden_dir, dev):
+    import argparse
+    from unmore_b200.object_scoring import Object_Scoring
+    g = _load(golden_dir, "scene_aa.npz")
+    fields = synth.make_fields(int(g["index"])).to(dev)
+    sc = Object_Scoring(argparse.Namespace(antialias=True), device=dev)
+    anns = sc.score_image(fields, g["discovered"].astype(np.float64).tolist(), image_id=int(g["index"]))
+    assert len(anns) == len(g["score_score"])
+    assert np.array_equal(np.array([a["bbox"] for a in anns], np.float32), g["score_bbox"])
+    for key in ("score", "existence_score", "center_score", "boundary_score", "area_score"):
+        assert_rel([a[key] for a in anns], g["score_" + key], key + " (antialias)")
+    masks = np.stack([a["segmentation"]["mask"] for a in anns])
+    packed = np.packbits(masks.reshape(len(anns), -1), axis=1, bitorder="little")
+    assert np.array_equal(packed, g["score_masks_packed"]), "binary masks must be bit-exact (antialias)"

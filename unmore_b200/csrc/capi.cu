@@ -200,6 +200,69 @@ int unmore_update_bbox_from_tiles(const float* tiles, int M, float* deltas_out, 
   return cuda_fail(launch_tiles(p, (cudaStream_t)stream), "tiles_kernel");
 }
 
+// ---- tile path (second resize mode, antialias=True): the same stages on PRE-RESAMPLED tiles -------------------------
+int unmore_tile_means(const float* tiles, long long tile_stride, int M, float* means_out, unmore_stream_t stream) {
+  if (M < 0 || tile_stride < 128 * 128 || (M > 0 && (!tiles || !means_out))) return fail(UNMORE_E_INVALID, "unmore_tile_means: bad argument");
+  return cuda_fail(launch_tile_means(tiles, tile_stride, M, means_out, (cudaStream_t)stream), "tile_means_kernel");
+}
+
+int unmore_center_reasoning_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes, int boxes_f64,
+                                       const int* counts, int cap, double center_score_max_thres, double* max_values_out,
+                                       int* argmax_out, double* splits_out, unsigned char* cc_counts_out,
+                                       double* cc_boxes_out, int* cc_overflow, void* ws, unmore_stream_t stream) {
+  if (!tiles || !boxes || !max_values_out || !argmax_out || !ws || cap < 0 || n_img <= 0 || H <= 0 || W <= 0)
+    return fail(UNMORE_E_INVALID, "unmore_center_reasoning_from_tiles: bad argument");
+  if (cap == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  CenterParams p{};
+  p.tiles = tiles; p.C = 3; p.H = H; p.W = W; p.ch_sdf = 0; p.ch_crow = 1; p.ch_ccol = 2;
+  p.boxes = boxes; p.boxes_f64 = boxes_f64; p.thr = center_score_max_thres;
+  p.max_values = max_values_out; p.argmax = argmax_out; p.splits = splits_out;
+  if ((cc_counts_out != nullptr) != (cc_boxes_out != nullptr) || (cc_counts_out != nullptr) != (cc_overflow != nullptr))
+    return fail(UNMORE_E_INVALID, "unmore_center_reasoning_from_tiles: the three analyze_cc outputs go together");
+  p.cc_counts = cc_counts_out; p.cc_boxes = cc_boxes_out; p.cc_overflow = cc_overflow;
+  anti_center_filter(p.filt);
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) {
+      const float f0 = (float)p.filt[i * 5 + j], f1 = (float)p.filt[j * 5 + i];
+      unsigned lo, hi;
+      memcpy(&lo, &f0, 4); memcpy(&hi, &f1, 4);
+      p.filt_pair[i * 5 + j] = ((unsigned long long)hi << 32) | lo;
+    }
+  if (int e = make_worklist(p.work, counts, n_img, cap, ws, s)) return e;
+  return cuda_fail(launch_center(p, num_sms(), s), "center_kernel (tiles)");
+}
+
+int unmore_boundary_round_from_tiles(const float* tiles, int M, const void* boxes, int boxes_f64, int H, int W,
+                                     float max_sdf_thres, float max_shrink_threshold, float delta_ratio, float* boxes_out,
+                                     float* labels_out, float* deltas_ws, float* max_ws, unmore_stream_t stream) {
+  if (M < 0 || H <= 0 || W <= 0 || (M > 0 && (!tiles || !boxes || !boxes_out || !labels_out || !deltas_ws || !max_ws)))
+    return fail(UNMORE_E_INVALID, "unmore_boundary_round_from_tiles: bad argument");
+  if (M == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  TileParams t{tiles, M, reinterpret_cast<float4*>(deltas_ws), max_ws};
+  if (int e = cuda_fail(launch_tiles(t, s), "tiles_kernel")) return e;
+  RefineParams p{};
+  p.H = H; p.W = W; p.boxes = boxes; p.boxes_f64 = boxes_f64;
+  p.max_sdf_thres = max_sdf_thres; p.max_shrink_thres = max_shrink_threshold; p.delta_ratio = delta_ratio;
+  p.boxes_out = reinterpret_cast<float4*>(boxes_out); p.labels_out = labels_out;
+  return cuda_fail(launch_round_update(p, reinterpret_cast<const float4*>(deltas_ws), max_ws, M, s), "round_update_kernel");
+}
+
+int unmore_score_and_rasterise_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes, int boxes_f64,
+                                          const int* counts, int cap, float* scores_out, float* tight_out, int* areas_out,
+                                          uint32_t* masks_out, unmore_stream_t stream) {
+  if (!tiles || !boxes || !scores_out || !tight_out || !areas_out || cap < 0 || n_img <= 0 || H <= 0 || W <= 0)
+    return fail(UNMORE_E_INVALID, "unmore_score_and_rasterise_from_tiles: bad argument");
+  if (n_img > 65535) return fail(UNMORE_E_CAPACITY, "unmore_score_and_rasterise_from_tiles: n_img > 65535 per call");
+  ScoreParams p{};
+  p.tiles = tiles; p.n_img = n_img; p.C = 4; p.H = H; p.W = W;
+  p.boxes = boxes; p.boxes_f64 = boxes_f64; p.counts = counts; p.cap = cap;
+  p.scores = reinterpret_cast<float4*>(scores_out); p.tight = reinterpret_cast<float4*>(tight_out);
+  p.areas = areas_out; p.masks = masks_out;
+  return cuda_fail(launch_score(p, (cudaStream_t)stream), "score_kernel (tiles)");
+}
+
 int unmore_cc_cap(void) { return UNMORE_CC_CAP; }
 
 int unmore_compact_boxes(const void* in, int in_f64, const int* counts_in, int cap_in, int group, int mode,

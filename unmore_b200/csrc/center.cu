@@ -205,6 +205,20 @@ struct CenterRows {
   }
 };
 
+// Row source over PRE-RESAMPLED tiles (PLANE_ELEMS = -1): [3, 128, 128] per proposal = (sdf, center_row, center_col),
+// e.g. from unmore_crop_resize_aa — the tile path of the second resize mode.  Same output contract as CenterRows::row.
+struct CenterTileRows {
+  const float* tile;
+  __device__ __forceinline__ void row(int lane, int i, float s[4], f32x2 ab[4]) const {
+    const float* r = tile + i * kCrop + lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      s[c] = __ldg(r + 32 * c);
+      ab[c] = pk2(__ldg(r + kCrop * kCrop + 32 * c), __ldg(r + 2 * kCrop * kCrop + 32 * c));
+    }
+  }
+};
+
 // PLANE_ELEMS: 0 = any field size / channel order; H*W = the three channels are consecutive planes of a field
 // of exactly that size (the COCO-val shape the batch path runs on), see MultiPlaneRows.
 constexpr int kSpecPlaneElems = 480 * 640;
@@ -279,8 +293,9 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       const float* base = p.fields + (size_t)img * p.C * plane_sz;
       const float* const planes[3] = {base + p.ch_sdf * plane_sz, base + p.ch_crow * plane_sz,
                                       base + p.ch_ccol * plane_sz};
-      CenterRows<PLANE_ELEMS> rows;
-      rows.init(planes, p.W, win);
+      CenterRows<(PLANE_ELEMS > 0 ? PLANE_ELEMS : 0)> rows;
+      CenterTileRows trows{PLANE_ELEMS < 0 ? p.tiles + row * (size_t)(3 * kCrop * kCrop) : nullptr};
+      if constexpr (PLANE_ELEMS >= 0) rows.init(planes, p.W, win);
       const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
       const int in_h = win.h();
       float cabs = 0.f;  // max |center field| over the tile (>= the staged window's): scales the fp32 screening margin
@@ -297,7 +312,8 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         const AxisTap v = axis_tap(scale_y, i, in_h);
         float s[4];
         f32x2 ab[4];
-        rows.row(taps, v, s, ab);
+        if constexpr (PLANE_ELEMS < 0) trows.row(lane, i, s, ab);
+        else rows.row(taps, v, s, ab);
         uint32_t word[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -700,6 +716,7 @@ static int launch_center_t(const CenterParams& p, int num_sms, cudaStream_t stre
 }
 
 int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
+  if (p.tiles) return p.cc_counts ? launch_center_t<true, -1>(p, num_sms, stream) : launch_center_t<false, -1>(p, num_sms, stream);
   const bool spec = p.H * p.W == kSpecPlaneElems && p.ch_crow == p.ch_sdf + 1 && p.ch_ccol == p.ch_sdf + 2;
   if (p.cc_counts) return spec ? launch_center_t<true, kSpecPlaneElems>(p, num_sms, stream) : launch_center_t<true, 0>(p, num_sms, stream);
   return spec ? launch_center_t<false, kSpecPlaneElems>(p, num_sms, stream) : launch_center_t<false, 0>(p, num_sms, stream);

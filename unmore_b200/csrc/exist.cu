@@ -259,6 +259,38 @@ int launch_crop_resize(const float* fields, int n_img, int C, int H, int W, cons
   return (int)cudaGetLastError();
 }
 
+// existence_checking on PRE-RESAMPLED tiles (the tile path of the second resize mode, antialias=True: the tiles come
+// from unmore_crop_resize_aa): score = mean of the [128,128] existence tile, summed in the same order as
+// existence_kernel (lane = columns l, l+32, l+64, l+96; fp32 partials flushed to fp64 every 8 rows).
+__global__ void __launch_bounds__(kExistWarps * 32) tile_means_kernel(const float* __restrict__ tiles, long long tile_stride,
+                                                                      int M, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * kExistWarps + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float* t = tiles + (size_t)m * tile_stride;
+  double acc = 0.0;
+  f32x2 part = pk2(0.f, 0.f);
+  for (int i = 0; i < kCrop; ++i) {
+    const float* r = t + i * kCrop + lane;
+    const f32x2 v0 = pk2(__ldg(r), __ldg(r + 32)), v1 = pk2(__ldg(r + 64), __ldg(r + 96));
+    part = add2(part, add2(v0, v1));
+    if ((i & 7) == 7) {
+      float lo, hi;
+      upk2(part, lo, hi);
+      acc += (double)(lo + hi);
+      part = pk2(0.f, 0.f);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[m] = (float)(acc * (1.0 / (kCrop * kCrop)));
+}
+
+int launch_tile_means(const float* tiles, long long tile_stride, int M, float* out, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  tile_means_kernel<<<(M + kExistWarps - 1) / kExistWarps, kExistWarps * 32, 0, stream>>>(tiles, tile_stride, M, out);
+  return (int)cudaGetLastError();
+}
+
 int launch_existence(const ExistParams& p, int num_sms, cudaStream_t stream) {
 #ifdef UNMORE_EXIST_TMA
   // bulk copies need 16-byte aligned rows: W % 4 == 0 and an aligned field stack; everything else takes the gather kernel

@@ -399,6 +399,39 @@ __global__ void __launch_bounds__(kRefineWarps * 32) tiles_kernel(const TilePara
   }
 }
 
+// One round of optimize_one_image_single_round (object_reasoning.py:421-479) AFTER the tile reductions: max_sdf
+// filter, label, asymmetric step, post_process_bbox_update and clip for M proposals whose deltas / max_sdf came from
+// tiles_kernel.  The tile path of the second resize mode (antialias=True): crop (unmore_crop_resize_aa) -> tiles ->
+// tiles_kernel -> this.  Same arithmetic as the fused kernel (apply_update), one thread per proposal.
+__global__ void __launch_bounds__(128) round_update_kernel(const RefineParams p, const float4* __restrict__ deltas,
+                                                           const float* __restrict__ max_sdf, int M) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double x1, y1, x2, y2;
+  load_box<double>(p.boxes, p.boxes_f64 != 0, (size_t)m, x1, y1, x2, y2);
+  const Window win = snap_window<double>(x1, y1, x2, y2, p.W, p.H);
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+  int lab = -1;
+  if (!win.empty() && max_sdf[m] > p.max_sdf_thres) {
+    const float4 dl = deltas[m];
+    Deltas d;
+    d.max_sdf = max_sdf[m]; d.dx1 = dl.x; d.dy1 = dl.y; d.dx2 = dl.z; d.dy2 = dl.w;
+    if (p.boxes_f64) {
+      lab = apply_update<double>(p, win, d, BoxT<double>{x1, y1, x2, y2}, nb);
+    } else {
+      lab = apply_update<float>(p, win, d, BoxT<float>{(float)x1, (float)y1, (float)x2, (float)y2}, nb);
+    }
+  }
+  p.boxes_out[m] = nb;
+  p.labels_out[m] = (float)lab;
+}
+
+int launch_round_update(const RefineParams& p, const float4* deltas, const float* max_sdf, int M, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  round_update_kernel<<<(M + 127) / 128, 128, 0, stream>>>(p, deltas, max_sdf, M);
+  return (int)cudaGetLastError();
+}
+
 int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream) {
   const int ctas = num_sms * UNMORE_REFINE_MINBLOCKS;  // resident CTAs per SM; warps pull proposals dynamically
   if (p.W == kSpecRowElems) refine_kernel<kSpecRowElems><<<ctas, kRefineWarps * 32, 0, stream>>>(p);

@@ -10,6 +10,7 @@
 // two CPU kernels bit for bit (generic kernel for h+w > 128, small-output kernel otherwise —
 // see common.cuh) because near-tie values decide mask bits.
 #include "resample.cuh"
+#include "resample_aa.cuh"
 #include "unmore_internal.h"
 
 namespace unmore {
@@ -50,6 +51,19 @@ __device__ __forceinline__ bool resized_mask_bit(const uint32_t m[kCrop][4], con
   return val > 0.5f;
 }
 
+// The same pixel in the second resize mode (antialias=True): ATen's separable antialiased kernel on the {0,1} mask,
+// horizontal pass first — T[yy][x] = sum_xx wx * bit(yy, xx) — then the vertical pass over T; every T value is
+// recomputed where it is needed (same arithmetic, same rounding as the two-pass form of resample_aa.cu).
+__device__ __forceinline__ bool resized_mask_bit_aa(const uint32_t m[kCrop][4], const AaAxis& ay, const AaAxis& ax, int y, int x) {
+  const float v = aa_dot(ay, y, [&](int yy) { return aa_dot(ax, x, [&](int xx) { return bit_at(m, yy, xx); }); });
+  return v > 0.5f;   // round half to even: exactly 0.5 -> 0
+}
+
+// TILES_AA = false: the fused primary path (crop + plain bilinear resample inside the kernel, antialias=False).
+// TILES_AA = true: the tile path of the second resize mode — the four channels come PRE-RESAMPLED from p.tiles
+// ([n_img * cap, 4, 128, 128] = sdf, center_row, center_col, existence, e.g. from unmore_crop_resize_aa) and the masks
+// are rasterised back to the box with the antialiased kernel.
+template <bool TILES_AA>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScoreSmem& sm = *reinterpret_cast<ScoreSmem*>(smem_raw);
@@ -77,13 +91,14 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
   // ---- 1. resample the four channels; warp w owns rows 16w .. 16w+15
   {
     ColTaps taps;
-    taps.init<kStrided>(lane, win.w());
+    if constexpr (!TILES_AA) taps.init<kStrided>(lane, win.w());
     const size_t plane_sz = (size_t)p.H * p.W;
     const float* base = p.fields + (size_t)img * p.C * plane_sz;
     const float* const planes[4] = {base + p.ch_sdf * plane_sz, base + p.ch_crow * plane_sz,
                                     base + p.ch_ccol * plane_sz, base + p.ch_exist * plane_sz};
     MultiPlaneRows<4> rows;
-    rows.init(planes, p.W, win);
+    if constexpr (!TILES_AA) rows.init(planes, p.W, win);
+    const float* tile = TILES_AA ? p.tiles + row * (size_t)(4 * kCrop * kCrop) : nullptr;
     const float scale_y = __fdiv_rn((float)win.h(), (float)kCrop);
     const int in_h = win.h();
     double esum = 0.0;
@@ -93,7 +108,14 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
       const int i = warp * kRows + ii;
       const AxisTap v = axis_tap(scale_y, i, in_h);
       float sabe[4][4];
-      rows.row(taps, v, sabe);
+      if constexpr (TILES_AA) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sabe[q][c] = __ldg(tile + (q * kCrop + i) * kCrop + lane + 32 * c);
+      } else {
+        rows.row(taps, v, sabe);
+      }
       const float (&s)[4] = sabe[0];
       const float (&a)[4] = sabe[1];
       const float (&b)[4] = sabe[2];
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
   // ---- 2. x taps of the resize back to the box (128 -> ow), shared by both masks
   const int ow = win.w(), oh = win.h();
   const float sx = __fdiv_rn((float)kCrop, (float)ow), sy = __fdiv_rn((float)kCrop, (float)oh);
-  for (int x = tid; x < ow; x += kScoreThreads) {
+  for (int x = tid; x < ow && !TILES_AA; x += kScoreThreads) {
     const AxisTap t = axis_tap(sx, x, kCrop);
     sm.tx0[x] = (unsigned char)t.i0; sm.tx1[x] = (unsigned char)t.i1; sm.tw0[x] = t.l0; sm.tw1[x] = t.l1;
   }
@@ -132,6 +154,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
   }
   // ---- 3. rasterise the union on the image canvas, one 32-pixel word per thread step
   const bool small_path = (oh + ow) <= 128;
+  AaAxis aax, aay;
+  if constexpr (TILES_AA) { aax.init(kCrop, ow); aay.init(kCrop, oh); }
   int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1, area = 0;
   for (int q = tid; q < p.H * Wp; q += kScoreThreads) {
     const int y = q / Wp, wx = q - y * Wp;
@@ -142,13 +166,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
       const int lo = max(xb, win.x1), hi = min(xb + 32, win.x2);
       for (int x = lo; x < hi; ++x) {
         const int ox = x - win.x1;
-        const int x0 = sm.tx0[ox], x1 = sm.tx1[ox];
-        const float w0 = sm.tw0[ox], w1 = sm.tw1[ox];
         bool on = false;
+        if constexpr (TILES_AA) {
+          on = resized_mask_bit_aa(sm.cmask, aay, aax, y - win.y1, ox) || resized_mask_bit_aa(sm.bmask, aay, aax, y - win.y1, ox);
+        } else {
+          const int x0 = sm.tx0[ox], x1 = sm.tx1[ox];
+          const float w0 = sm.tw0[ox], w1 = sm.tw1[ox];
 #pragma unroll
-        for (int mm = 0; mm < 2; ++mm) {
-          const uint32_t (*m)[4] = mm == 0 ? sm.cmask : sm.bmask;
-          on = on || resized_mask_bit(m, ty, x0, x1, w0, w1, small_path);
+          for (int mm = 0; mm < 2; ++mm) {
+            const uint32_t (*m)[4] = mm == 0 ? sm.cmask : sm.bmask;
+            on = on || resized_mask_bit(m, ty, x0, x1, w0, w1, small_path);
+          }
         }
         word |= (on ? 1u : 0u) << (x - xb);
       }
@@ -216,10 +244,16 @@ int launch_mask_resize(const unsigned char* masks, int B, int oh, int ow, unsign
 
 int launch_score(const ScoreParams& p, cudaStream_t stream) {
   if (p.n_img <= 0 || p.cap <= 0) return 0;
-  cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem));
-  if (e != cudaSuccess) return (int)e;
   dim3 grid(p.cap, p.n_img);
-  score_kernel<<<grid, kScoreThreads, sizeof(ScoreSmem), stream>>>(p);
+  if (p.tiles) {
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem));
+    if (e != cudaSuccess) return (int)e;
+    score_kernel<true><<<grid, kScoreThreads, sizeof(ScoreSmem), stream>>>(p);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScoreSmem));
+    if (e != cudaSuccess) return (int)e;
+    score_kernel<false><<<grid, kScoreThreads, sizeof(ScoreSmem), stream>>>(p);
+  }
   return (int)cudaGetLastError();
 }
 

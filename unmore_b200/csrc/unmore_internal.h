@@ -35,6 +35,7 @@ struct TileParams {
 };
 int launch_refine(const RefineParams& p, int num_sms, cudaStream_t stream);
 int launch_tiles(const TileParams& p, cudaStream_t stream);
+int launch_round_update(const RefineParams& p, const float4* deltas, const float* max_sdf, int M, cudaStream_t stream);
 
 // ---- exist.cu ------------------------------------------------------------------------
 struct ExistParams {
@@ -46,6 +47,7 @@ struct ExistParams {
   float* scores;  // [n_img, cap]
 };
 int launch_existence(const ExistParams& p, int num_sms, cudaStream_t stream);
+int launch_tile_means(const float* tiles, long long tile_stride, int M, float* out, cudaStream_t stream);
 int launch_crop_resize(const float* fields, int n_img, int C, int H, int W, const int* channels, int n_ch,
                        const void* boxes, int boxes_f64, const int* counts, int cap, float* out, cudaStream_t stream);
 
@@ -59,6 +61,7 @@ int launch_mask_resize_aa(const unsigned char* masks, int B, int oh, int ow, uns
 #define UNMORE_CC_CAP 16   // connected-component boxes kept per proposal (--analyze_cc); overflow is counted
 #endif
 struct CenterParams {
+  const float* tiles;   // nullable: pre-resampled [n_img * cap, 3, 128, 128] (sdf, center_row, center_col) instead of `fields`
   const float* fields;
   int C, H, W, ch_sdf, ch_crow, ch_ccol;
   const void* boxes;
@@ -128,6 +131,7 @@ int launch_box_nms(const NmsParams& p, cudaStream_t stream);
 
 // ---- score.cu ------------------------------------------------------------------------
 struct ScoreParams {
+  const float* tiles;  // nullable: pre-resampled [n_img * cap, 4, 128, 128] (sdf, center_row, center_col, existence); selects the antialiased rasteriser
   const float* fields;
   int n_img, C, H, W, ch_sdf, ch_crow, ch_ccol, ch_exist;
   const void* boxes;   // [n_img, cap, 4]

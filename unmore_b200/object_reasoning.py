@@ -142,6 +142,9 @@ class Object_Discovery:
         boxes = self._boxes(proposals)
         if boxes.shape[1] == 0:
             return {"existence_scores": torch.zeros((0,), dtype=torch.float32)}
+        if self.antialias:   # tile path: antialiased crops of the existence channel, then their means
+            tiles = ops.crop_resize(self._fields(image), boxes, [self.channels.exist], antialias=True)
+            return {"existence_scores": ops.tile_means(tiles[0, :, 0]).cpu()}
         scores = ops.existence_scores(self._fields(image), boxes, ch=self.channels)
         return {"existence_scores": scores[0].cpu()}
 
@@ -163,8 +166,15 @@ class Object_Discovery:
             e = torch.zeros((0, 4), dtype=torch.float64, device=self.device)
             return {"proposals_pass_singularity": e, "splited_new_proposals": e.clone()}
         cc_on = bool(getattr(self.args, "analyze_cc", False))
-        _, argmax, splits, cc = ops.center_reasoning(self._fields(image), boxes, thr=self.args.center_score_max_thres,
-                                                     ch=self.channels, analyze_cc=cc_on)
+        if self.antialias:
+            f = self._fields(image)
+            ch = self.channels
+            tiles = ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col], antialias=True)
+            _, argmax, splits, cc = ops.center_reasoning_from_tiles(tiles, f.shape[-2], f.shape[-1], boxes,
+                                                                    thr=self.args.center_score_max_thres, analyze_cc=cc_on)
+        else:
+            _, argmax, splits, cc = ops.center_reasoning(self._fields(image), boxes, thr=self.args.center_score_max_thres,
+                                                         ch=self.channels, analyze_cc=cc_on)
         fail = argmax[0] >= 0
         new = splits[0][fail].reshape(-1, 4)
         if cc_on:
@@ -184,7 +194,7 @@ class Object_Discovery:
         """Un-eroded union masks (object_reasoning.py:528-531) of ``boxes`` [1,K,4] as [K,128,128] u8, from the
         bit-exact resized crops and the same thresholds the center kernel applies (common.cuh)."""
         ch = self.channels
-        crops = ops.crop_resize(fields, boxes.contiguous(), [ch.sdf, ch.center_row, ch.center_col])[0]
+        crops = ops.crop_resize(fields, boxes.contiguous(), [ch.sdf, ch.center_row, ch.center_col], antialias=self.antialias)[0]
         sq = crops[:, 1] * crops[:, 1] + crops[:, 2] * crops[:, 2]
         return ((crops[:, 0] > 8.94069671630859375e-08) | (sq > 0.2500000298023223876953125)).to(torch.uint8)
 
@@ -283,6 +293,12 @@ class Object_Discovery:
             return {"updated_bboxes": torch.zeros((0, 4), dtype=torch.float32, device=self.device),
                     "labels": torch.zeros((0,), dtype=torch.float32, device=self.device)}
         a = self.args
+        if self.antialias:
+            f = self._fields(image)
+            tiles = ops.crop_resize(f, boxes, [self.channels.sdf], antialias=True)[0, :, 0]
+            out, lab = ops.boundary_round_from_tiles(tiles, boxes[0], f.shape[-2], f.shape[-1], max_sdf_thres=a.max_sdf_thres,
+                                                     max_shrink_threshold=a.max_shrink_threshold, delta_ratio=a.delta_ratio)
+            return {"updated_bboxes": out, "labels": lab}
         out, lab, _ = ops.boundary_refine(self._fields(image), boxes, n_round=1, apply_small_filter=False,
                                           early_exit=False, proposal_area_thres=a.proposal_area_thres,
                                           max_sdf_thres=a.max_sdf_thres, max_shrink_threshold=a.max_shrink_threshold,
@@ -298,6 +314,8 @@ class Object_Discovery:
         if boxes.shape[1] == 0:
             return {"proposals": [], "labels": []}
         a = self.args
+        if self.antialias:
+            return self._boundary_reasoning_tiles(self._fields(image), boxes[0])
         out, lab, _ = ops.boundary_refine(self._fields(image), boxes, n_round=a.n_round, apply_small_filter=True,
                                           early_exit=True, proposal_area_thres=a.proposal_area_thres,
                                           max_sdf_thres=a.max_sdf_thres, max_shrink_threshold=a.max_shrink_threshold,
@@ -307,6 +325,39 @@ class Object_Discovery:
             return {"proposals": [], "labels": []}
         return {"proposals": out[0][in_list], "labels": lab[0][in_list]}
 
+    def _boundary_reasoning_tiles(self, f: torch.Tensor, cur: torch.Tensor):
+        """boundary_reasoning (object_reasoning.py:582-612) in the second resize mode: the round loop runs on the
+        host like the reference's, every round is crop (antialiased) -> tiles -> tile reductions -> box update on the
+        device.  Rows that reached label 1 with an unchanged box are exact fixed points and are not recomputed."""
+        a = self.args
+        H, W = f.shape[-2], f.shape[-1]
+        labels = torch.zeros((cur.shape[0],), dtype=torch.float32, device=self.device)
+        fixed = torch.zeros((cur.shape[0],), dtype=torch.bool, device=self.device)
+        for _ in range(a.n_round):
+            area = (cur[:, 2] - cur[:, 0]) * (cur[:, 3] - cur[:, 1])          # filter_small_proposal (:293-299), in cur's dtype
+            keep = area > a.proposal_area_thres
+            cur, labels, fixed = cur[keep], labels[keep], fixed[keep]
+            if cur.shape[0] == 0:
+                return {"proposals": [], "labels": []}
+            act = ~fixed
+            new = cur.to(torch.float32).clone()
+            newl = labels.clone()
+            if bool(act.any()):
+                boxes = cur[act].contiguous()
+                tiles = ops.crop_resize(f, boxes[None].contiguous(), [self.channels.sdf], antialias=True)[0, :, 0]
+                out, lab = ops.boundary_round_from_tiles(tiles, boxes, H, W, max_sdf_thres=a.max_sdf_thres,
+                                                         max_shrink_threshold=a.max_shrink_threshold, delta_ratio=a.delta_ratio)
+                new[act] = out
+                newl[act] = lab
+                same = (out.to(cur.dtype) == boxes).all(dim=1) & (lab == 1)
+                fx = fixed.clone()
+                fx[act] = same
+                fixed = fx
+            cur, labels = new, newl
+            if bool(fixed.all()):
+                break
+        return {"proposals": cur, "labels": labels}
+
     # ---- main loop body ---------------------------------------------------------------
     def discover_image(self, image, proposals=None) -> np.ndarray:
         """Loop body of main_object_discovery (object_reasoning.py:618-662) for one image:
@@ -315,8 +366,41 @@ class Object_Discovery:
         if proposals is None:
             proposals = self.generate_random_proposal(f.shape[-2], f.shape[-1])
         boxes = self._boxes(proposals)
+        if self.antialias:
+            return self._discover_image_tiles(f[0], boxes[0])
         det, cnt = self.discover_batch(f, boxes)
         return det[0, : int(cnt[0])].cpu().numpy()
+
+    def _discover_image_tiles(self, image: torch.Tensor, proposals: torch.Tensor) -> np.ndarray:
+        """The loop body of main_object_discovery (:623-662) in the second resize mode, stage by stage through the
+        reference-named methods (each one on the tile path); empty intermediate lists end the image like the
+        reference's ``continue``s (and an empty split list is 'no splits' instead of the reference's crash)."""
+        a = self.args
+        empty = np.zeros((0, 4), dtype=np.float32)
+        ex = self.existence_checking(image, proposals)["existence_scores"].to(self.device)
+        proposals = proposals[ex >= a.class_score_thres]
+        if len(proposals) == 0:
+            return empty
+        cr = self.center_reasoning(image, proposals)
+        p_pass, split = cr["proposals_pass_singularity"], cr["splited_new_proposals"]
+        if len(split) > 0:
+            ex2 = self.existence_checking(image, split)["existence_scores"].to(self.device)
+            split = split[ex2 >= a.class_score_thres]
+        if len(split) > 0:
+            cr2 = self.center_reasoning(image, split)
+            proposals = torch.cat((p_pass, cr2["proposals_pass_singularity"]), dim=0)
+        else:
+            proposals = p_pass
+        if len(proposals) == 0:
+            return empty
+        br = self.boundary_reasoning(image, proposals)
+        if len(br["proposals"]) == 0:
+            return empty
+        final = br["proposals"][br["labels"] == 1]
+        if len(final) == 0:
+            return empty
+        keep, kc, kb = ops.box_nms(final.to(torch.float32)[None].contiguous(), None, None, iou_threshold=0.5)
+        return kb[0, : int(kc[0])].cpu().numpy()
 
     def discover_batch(self, fields: torch.Tensor, proposals: torch.Tensor, counts: Optional[torch.Tensor] = None,
                        stats: Optional[dict] = None):
@@ -330,6 +414,16 @@ class Object_Discovery:
         B, N = proposals.shape[0], proposals.shape[1]
         dev = fields.device
         f64 = torch.float64
+        if self.antialias:   # second resize mode: image by image on the tile path (not the batched fused kernels)
+            dets = [self._discover_image_tiles(fields[b], proposals[b] if counts is None else proposals[b, : int(counts[b])])
+                    for b in range(B)]
+            cap = max([len(d) for d in dets] + [1])
+            kb = torch.zeros((B, cap, 4), dtype=torch.float32, device=dev)
+            kc = torch.tensor([len(d) for d in dets], dtype=torch.int32, device=dev)
+            for b, d in enumerate(dets):
+                if len(d):
+                    kb[b, : len(d)] = torch.as_tensor(d, device=dev)
+            return kb, kc
         ws = ops.workspace(B, dev)
         # Step 1: existence checking (:627-630)
         ex = ops.existence_scores(fields, proposals, counts, ch=ch, ws=ws)

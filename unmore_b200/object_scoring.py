@@ -44,6 +44,8 @@ class Object_Scoring:
         self.raw_annotations = raw_annotations if raw_annotations is not None else {}
         self.test_dataset = test_dataset
         self.result_folder = result_folder
+        # resize mode (see Object_Discovery.antialias): True = the tile path with ATen's antialiased kernels
+        self.antialias = bool(getattr(self.args, "antialias", False))
         if raw_annotations is None and getattr(self.args, "raw_annotations_path", None):
             self.load_raw_annotations()
 
@@ -64,6 +66,10 @@ class Object_Scoring:
         boxes = torch.as_tensor(np.asarray(proposals, dtype=np.float64)).reshape(1, -1, 4).to(self.device)
         ch = self.channels
         f = self._fields(image)
+        if self.antialias:
+            crops = ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col, ch.exist], antialias=True)[0]
+            return {"pred_boundary_fields": crops[:, 0], "pred_center_fields": crops[:, 1:3],
+                    "pred_existence_scores": ops.tile_means(crops[:, 3])}
         crops = ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col])[0]
         return {"pred_boundary_fields": crops[:, 0], "pred_center_fields": crops[:, 1:3],
                 "pred_existence_scores": ops.existence_scores(f, boxes, ch=ch)[0]}
@@ -74,7 +80,13 @@ class Object_Scoring:
         order: out [B,cap,5] fp64 (score, existence, center, boundary, area_score), bbox [B,cap,4] xywh,
         selected [B,cap] (post_process predicate), keep [B,cap], keep_counts [B], masks (packed, indexed by
         the ORIGINAL proposal index: use keep to gather)."""
-        scores, tight, areas, masks = ops.score_and_rasterise(fields, boxes, counts, ch=self.channels, want_masks=want_masks)
+        if self.antialias:
+            ch = self.channels
+            tiles = ops.crop_resize(fields, boxes, [ch.sdf, ch.center_row, ch.center_col, ch.exist], counts, antialias=True)
+            scores, tight, areas, masks = ops.score_and_rasterise_from_tiles(tiles, fields.shape[-2], fields.shape[-1], boxes, counts,
+                                                                             want_masks=want_masks)
+        else:
+            scores, tight, areas, masks = ops.score_and_rasterise(fields, boxes, counts, ch=self.channels, want_masks=want_masks)
         keep, kc, _ = ops.box_nms(tight, scores[:, :, 2].contiguous(), counts, iou_threshold=0.5, want_boxes=False)
         out, bbox, sel = ops.final_scores(scores, tight, areas, keep, kc, self.args.existence_score_thres,
                                           self.args.center_score_thres, self.args.boundary_score_thres)

@@ -79,7 +79,8 @@ _KERNELS = {"unmore_crop_resize": 1, "unmore_crop_resize_aa": 2, "unmore_mask_re
             "unmore_batch_erode": 1, "unmore_anti_center_map": 1, "unmore_connected_components": 1, "unmore_box_nms_matrix": 3,
             "unmore_score_and_rasterise": 1, "unmore_mask_resize": 1, "unmore_final_scores": 1, "unmore_sat_build": 1, "unmore_sat_build_fields": 1, "unmore_box_sums": 1,
             "unmore_mask_pack": 1, "unmore_mask_stats": 1, "unmore_mask_nms": 3, "unmore_mask_rle_counts": 1,
-            "unmore_pack_detections": 1}
+            "unmore_pack_detections": 1, "unmore_tile_means": 1, "unmore_center_reasoning_from_tiles": 1,
+            "unmore_boundary_round_from_tiles": 2, "unmore_score_and_rasterise_from_tiles": 1}
 
 
 def set_timer(t: Optional[StageTimer]):
@@ -476,3 +477,85 @@ def pack_detections(image_ids: torch.Tensor, bbox: torch.Tensor, out5: torch.Ten
         _call("unmore_pack_detections", image_ids.data_ptr(), bbox.data_ptr(), out5.data_ptr(), keep_counts.data_ptr(), cap, B,
               rows.data_ptr(), rows.shape[0] - 1, _stream())
     return rows
+
+
+# ---- the tile path of the second resize mode (antialias=True): the stages on pre-resampled tiles ----------------------
+def tile_means(tiles: torch.Tensor) -> torch.Tensor:
+    """[M, 128, 128] fp32 tiles (dim-0 stride free, the tile itself contiguous) -> their means [M] (a3 on tiles)."""
+    if not tiles.is_cuda or tiles.dtype != torch.float32 or tiles.dim() != 3 or tiles.shape[1:] != (CROP, CROP) or \
+            tiles.stride(2) != 1 or tiles.stride(1) != CROP:
+        raise _lib.UnmoreError("tile_means needs CUDA fp32 [M, 128, 128] with contiguous tiles")
+    M = tiles.shape[0]
+    out = torch.zeros((M,), dtype=torch.float32, device=tiles.device)
+    _on(tiles)
+    if M:
+        _call("unmore_tile_means", tiles.data_ptr(), int(tiles.stride(0)), M, out.data_ptr(), _stream())
+    return out
+
+
+def center_reasoning_from_tiles(tiles, H, W, boxes, counts=None, thr: float = 0.009, ws=None, want_splits: bool = True,
+                                analyze_cc: bool = False):
+    """center_reasoning on tiles [n_img, cap, 3, 128, 128] = (sdf, center_row, center_col); same returns as
+    ``center_reasoning``.  H, W: image size (the --analyze_cc enlargement clips against it)."""
+    tiles = _on(tiles.contiguous())
+    n_img, cap = tiles.shape[0], tiles.shape[1]
+    _, f64 = _check_boxes(boxes, n_img)
+    _check_counts(counts, n_img)
+    dev = tiles.device
+    ws = workspace(n_img, dev) if ws is None else ws
+    maxv = torch.zeros((n_img, cap), dtype=torch.float64, device=dev)
+    argmax = torch.full((n_img, cap), -1, dtype=torch.int32, device=dev)
+    splits = torch.zeros((n_img, cap, 4, 4), dtype=torch.float64, device=dev) if want_splits else None
+    cc = None
+    if analyze_cc:
+        cc_cap = _lib.load().unmore_cc_cap()
+        cc = (torch.zeros((n_img, cap), dtype=torch.uint8, device=dev),
+              torch.zeros((n_img, cap, cc_cap, 4), dtype=torch.float64, device=dev),
+              torch.zeros((1,), dtype=torch.int32, device=dev))
+    _on(tiles)
+    if cap:
+        _call("unmore_center_reasoning_from_tiles", tiles.data_ptr(), n_img, int(H), int(W), boxes.data_ptr(), f64, _ptr(counts), cap,
+              float(thr), maxv.data_ptr(), argmax.data_ptr(), _ptr(splits), _ptr(cc[0]) if cc else None,
+              _ptr(cc[1]) if cc else None, _ptr(cc[2]) if cc else None, ws.data_ptr(), _stream(), counts=counts)
+    return maxv, argmax, splits, cc
+
+
+def boundary_round_from_tiles(tiles, boxes, H, W, max_sdf_thres: float = 0.5, max_shrink_threshold: float = 16.0,
+                              delta_ratio: float = 0.5):
+    """One round of optimize_one_image_single_round on sdf tiles [M, 128, 128] and their boxes [M, 4] (fp64 or fp32):
+    -> (updated boxes [M, 4] fp32, labels [M] fp32 in {-1, 0, 1})."""
+    tiles = _on(tiles.contiguous())
+    M = tiles.shape[0]
+    boxes = boxes.contiguous()
+    if boxes.shape != (M, 4) or boxes.dtype not in (torch.float32, torch.float64):
+        raise _lib.UnmoreError("boundary_round_from_tiles: boxes must be [M, 4] fp32 / fp64")
+    dev = tiles.device
+    out = torch.zeros((M, 4), dtype=torch.float32, device=dev)
+    lab = torch.full((M,), -1.0, dtype=torch.float32, device=dev)
+    if M:
+        dws = torch.empty((M, 4), dtype=torch.float32, device=dev)
+        mws = torch.empty((M,), dtype=torch.float32, device=dev)
+        _on(tiles)
+        _call("unmore_boundary_round_from_tiles", tiles.data_ptr(), M, boxes.data_ptr(), int(boxes.dtype == torch.float64), int(H), int(W),
+              float(max_sdf_thres), float(max_shrink_threshold), float(delta_ratio), out.data_ptr(), lab.data_ptr(),
+              dws.data_ptr(), mws.data_ptr(), _stream())
+    return out, lab
+
+
+def score_and_rasterise_from_tiles(tiles, H, W, boxes, counts=None, want_masks: bool = True):
+    """score_and_rasterise on tiles [n_img, cap, 4, 128, 128] = (sdf, center_row, center_col, existence); the masks are
+    resized back to the box with the ANTIALIASED kernel.  Same returns as ``score_and_rasterise``."""
+    tiles = _on(tiles.contiguous())
+    n_img, cap = tiles.shape[0], tiles.shape[1]
+    _, f64 = _check_boxes(boxes, n_img)
+    _check_counts(counts, n_img)
+    dev = tiles.device
+    scores = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
+    tight = torch.zeros((n_img, cap, 4), dtype=torch.float32, device=dev)
+    areas = torch.zeros((n_img, cap), dtype=torch.int32, device=dev)
+    masks = torch.zeros((n_img, cap, H, (W + 31) // 32), dtype=torch.int32, device=dev) if want_masks else None
+    _on(tiles)
+    if cap > 0:
+        _call("unmore_score_and_rasterise_from_tiles", tiles.data_ptr(), n_img, int(H), int(W), boxes.data_ptr(), f64, _ptr(counts), cap,
+              scores.data_ptr(), tight.data_ptr(), areas.data_ptr(), _ptr(masks), _stream())
+    return scores, tight, areas, masks
