@@ -409,6 +409,8 @@ def main():
         pass
     for name, k in kernels.items():
         k["traffic"] = prof.get("dram_bytes_per_launch", {}).get(name)
+        if name == "unmore_sat_build_fields" and n_img != 5000:
+            k["traffic"] = None    # the SAT capture is of the whole 5000-image batch (one launch of 10 000 planes)
         if name in prof.get("issue_active", {}):
             k["issue_active"] = prof["issue_active"][name]
     # the on-chip roofline of the refine kernel: its fields are L2-resident by construction (HBM frac << 1%), the
