@@ -456,6 +456,7 @@ def main():
         h_props = torch.from_numpy(props_np).pin_memory()
         torch.cuda.synchronize()
         copy_stream = torch.cuda.Stream()
+        side_stream = torch.cuda.Stream()
         bufs = [(torch.empty((chunk, 4, Hc, Wc), dtype=torch.float32, device=dev),
                  torch.empty((chunk, n_prop, 4), dtype=torch.float64, device=dev)) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
@@ -483,7 +484,29 @@ def main():
                     ready[j % 2].record(copy_stream)
                 return (c1 - c0) * (4 * px * 4 + n_prop * 32)
 
+            rle_stream = side_stream
+            done_ev = [torch.cuda.Event() for _ in chunks]
+
+            def read_back(j, r):
+                """COCO run lengths of the kept masks of chunk j (NMS order) on the SIDE stream, then their device -> host
+                read: the host blocks here while the main stream is already running chunk j + 1."""
+                nonlocal d2h, n_rle
+                with torch.cuda.stream(rle_stream):
+                    rle_stream.wait_event(done_ev[j])
+                    B, cap = r["keep"].shape
+                    valid = torch.arange(cap, device=dev)[None, :] < r["keep_counts"][:, None]
+                    flat = (torch.arange(B, device=dev)[:, None] * cap + r["keep"].clamp_min(0))[valid]
+                    km = r["masks"].view(B * cap, Hc, -1).index_select(0, flat)
+                    cnt, nr = ops.mask_rle_counts(km, Wc, MAX_RUNS)
+                    hc, hn = cnt.cpu(), nr.cpu()
+                    for t_ in (r["keep"], r["keep_counts"], r["masks"]):
+                        t_.record_stream(rle_stream)
+                d2h += hc.numel() * 4 + hn.numel() * 4
+                n_rle += int(hn.numel())
+                host_rle.append((hc, hn))
+
             h2d += issue(0)
+            prev = None
             for j, c0 in enumerate(chunks):
                 c1 = min(c0 + chunk, n_img)
                 if j + 1 < len(chunks):
@@ -493,17 +516,12 @@ def main():
                 r = pipe.run_chunk(fb[: c1 - c0], pb[: c1 - c0])
                 ops.pack_detections(image_ids[c0:c1], r["bbox"], r["out"], r["keep_counts"], rows)
                 freed[j % 2].record(torch.cuda.current_stream())
-                if with_rle:
-                    # run lengths of the kept masks of this chunk, NMS order; read back with their lengths
-                    B, cap = r["keep"].shape
-                    valid = torch.arange(cap, device=dev)[None, :] < r["keep_counts"][:, None]
-                    flat = (torch.arange(B, device=dev)[:, None] * cap + r["keep"].clamp_min(0))[valid]
-                    km = r["masks"].view(B * cap, Hc, -1).index_select(0, flat)
-                    cnt, nr = ops.mask_rle_counts(km, Wc, MAX_RUNS)
-                    hc, hn = cnt.cpu(), nr.cpu()     # device -> host read of the chunk's segmentations
-                    d2h += hc.numel() * 4 + hn.numel() * 4
-                    n_rle += int(hn.numel())
-                    host_rle.append((hc, hn))
+                done_ev[j].record(torch.cuda.current_stream())
+                if with_rle and prev is not None:
+                    read_back(*prev)
+                prev = (j, r)
+            if with_rle and prev is not None:
+                read_back(*prev)
             g2 = gather_rows(rows)
             m2, t2 = merge_rows(g2)
             hr = m2[: int(t2.item())].cpu()          # device -> host read of the detection rows
