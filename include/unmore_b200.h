@@ -80,7 +80,9 @@ int unmore_mask_resize_aa(const unsigned char* masks, int B, int H, int W, int o
  *   unmore_boundary_round_from_tiles       tiles [M, 128,128] (sdf) + boxes [M,4] -> updated boxes fp32 / labels
  *                                          (a10-a12 of ONE round; deltas_ws [M,4] and max_ws [M] are scratch)
  *   unmore_score_and_rasterise_from_tiles  tiles [n_img*cap, 4, 128,128] = (sdf, center_row, center_col, existence);
- *                                          the masks are resized back to the box with the antialiased kernel (a15) */
+ *                                          existence_scores (nullable) [n_img, cap]: per-crop classifier outputs used
+ *                                          instead of the mean of the fourth tile; antialias selects the kernel that
+ *                                          resizes the masks back to the box (a15) */
 int unmore_tile_means(const float* tiles, long long tile_stride, int M, float* means_out, unmore_stream_t stream);
 int unmore_center_reasoning_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes,
                                        int boxes_f64, const int* counts, int cap,
@@ -92,10 +94,10 @@ int unmore_boundary_round_from_tiles(const float* tiles, int M, const void* boxe
                                      float max_sdf_thres, float max_shrink_threshold, float delta_ratio,
                                      float* boxes_out, float* labels_out, float* deltas_ws, float* max_ws,
                                      unmore_stream_t stream);
-int unmore_score_and_rasterise_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes,
-                                          int boxes_f64, const int* counts, int cap, float* scores_out,
-                                          float* tight_out, int* areas_out, uint32_t* masks_out,
-                                          unmore_stream_t stream);
+int unmore_score_and_rasterise_from_tiles(const float* tiles, const float* existence_scores, int antialias,
+                                          int n_img, int H, int W, const void* boxes, int boxes_f64,
+                                          const int* counts, int cap, float* scores_out, float* tight_out,
+                                          int* areas_out, uint32_t* masks_out, unmore_stream_t stream);
 
 /* center_reasoning — object_reasoning.py:525-580 with batch_erode (utils/misc.py:10-20) and
  * center_field_to_anti_center_map (object_reasoning.py:360-377) fused.

@@ -25,7 +25,7 @@ SIGNATURES = {
     "unmore_tile_means": [_p, C.c_longlong, _i, _p, _p],
     "unmore_center_reasoning_from_tiles": [_p, _i, _i, _i, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p],
     "unmore_boundary_round_from_tiles": [_p, _i, _p, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p],
-    "unmore_score_and_rasterise_from_tiles": [_p, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
+    "unmore_score_and_rasterise_from_tiles": [_p, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p],
     "unmore_center_reasoning": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p],
     "unmore_boundary_refine": [_p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _i, _i, _i, _f, _f, _f, _f, _p, _p, _p, _p, _p],
     "unmore_update_bbox_from_tiles": [_p, _i, _p, _p, _p],

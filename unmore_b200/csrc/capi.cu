@@ -249,14 +249,15 @@ int unmore_boundary_round_from_tiles(const float* tiles, int M, const void* boxe
   return cuda_fail(launch_round_update(p, reinterpret_cast<const float4*>(deltas_ws), max_ws, M, s), "round_update_kernel");
 }
 
-int unmore_score_and_rasterise_from_tiles(const float* tiles, int n_img, int H, int W, const void* boxes, int boxes_f64,
-                                          const int* counts, int cap, float* scores_out, float* tight_out, int* areas_out,
-                                          uint32_t* masks_out, unmore_stream_t stream) {
+int unmore_score_and_rasterise_from_tiles(const float* tiles, const float* existence_scores, int antialias, int n_img, int H,
+                                          int W, const void* boxes, int boxes_f64, const int* counts, int cap,
+                                          float* scores_out, float* tight_out, int* areas_out, uint32_t* masks_out,
+                                          unmore_stream_t stream) {
   if (!tiles || !boxes || !scores_out || !tight_out || !areas_out || cap < 0 || n_img <= 0 || H <= 0 || W <= 0)
     return fail(UNMORE_E_INVALID, "unmore_score_and_rasterise_from_tiles: bad argument");
   if (n_img > 65535) return fail(UNMORE_E_CAPACITY, "unmore_score_and_rasterise_from_tiles: n_img > 65535 per call");
   ScoreParams p{};
-  p.tiles = tiles; p.n_img = n_img; p.C = 4; p.H = H; p.W = W;
+  p.tiles = tiles; p.exist_scores = existence_scores; p.aa_raster = antialias; p.n_img = n_img; p.C = 4; p.H = H; p.W = W;
   p.boxes = boxes; p.boxes_f64 = boxes_f64; p.counts = counts; p.cap = cap;
   p.scores = reinterpret_cast<float4*>(scores_out); p.tight = reinterpret_cast<float4*>(tight_out);
   p.areas = areas_out; p.masks = masks_out;

@@ -60,9 +60,11 @@ __device__ __forceinline__ bool resized_mask_bit_aa(const uint32_t m[kCrop][4], 
 }
 
 // TILES_AA = false: the fused primary path (crop + plain bilinear resample inside the kernel, antialias=False).
-// TILES_AA = true: the tile path of the second resize mode — the four channels come PRE-RESAMPLED from p.tiles
-// ([n_img * cap, 4, 128, 128] = sdf, center_row, center_col, existence, e.g. from unmore_crop_resize_aa) and the masks
-// are rasterised back to the box with the antialiased kernel.
+// TILES_AA = true: the tile path — the four channels come PRE-RESAMPLED from p.tiles ([n_img * cap, 4, 128, 128] = sdf,
+// center_row, center_col, existence: from unmore_crop_resize_aa in the second resize mode, or from the per-crop nets
+// of the reference's original mode); the masks are rasterised back to the box with the antialiased kernel when
+// p.aa_raster is set and with the plain one otherwise; p.exist_scores, when given, replaces the mean of the fourth
+// tile (the reference's classifier puts out one scalar per crop, object_scoring.py:140-150).
 template <bool TILES_AA>
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,7 +142,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
   // ---- 2. x taps of the resize back to the box (128 -> ow), shared by both masks
   const int ow = win.w(), oh = win.h();
   const float sx = __fdiv_rn((float)kCrop, (float)ow), sy = __fdiv_rn((float)kCrop, (float)oh);
-  for (int x = tid; x < ow && !TILES_AA; x += kScoreThreads) {
+  const bool aa_raster = TILES_AA && p.aa_raster;
+  for (int x = tid; x < ow && !aa_raster; x += kScoreThreads) {
     const AxisTap t = axis_tap(sx, x, kCrop);
     sm.tx0[x] = (unsigned char)t.i0; sm.tx1[x] = (unsigned char)t.i1; sm.tw0[x] = t.l0; sm.tw1[x] = t.l1;
   }
@@ -150,12 +153,13 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
     float cm = 0.f, bm = -INFINITY;
     for (int w = 0; w < kScoreWarps; ++w) { es += sm.red_sum[w]; cm = fmaxf(cm, sm.red_c[w]); bm = fmaxf(bm, sm.red_b[w]); }
     // (existence, center, boundary, unused)
-    p.scores[row] = make_float4((float)(es * (1.0 / (kCrop * kCrop))), __fsqrt_rn(cm), bm, 0.f);
+    const float ex = (TILES_AA && p.exist_scores) ? p.exist_scores[row] : (float)(es * (1.0 / (kCrop * kCrop)));
+    p.scores[row] = make_float4(ex, __fsqrt_rn(cm), bm, 0.f);
   }
   // ---- 3. rasterise the union on the image canvas, one 32-pixel word per thread step
   const bool small_path = (oh + ow) <= 128;
   AaAxis aax, aay;
-  if constexpr (TILES_AA) { aax.init(kCrop, ow); aay.init(kCrop, oh); }
+  if (aa_raster) { aax.init(kCrop, ow); aay.init(kCrop, oh); }
   int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1, area = 0;
   for (int q = tid; q < p.H * Wp; q += kScoreThreads) {
     const int y = q / Wp, wx = q - y * Wp;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const ScoreParams 
       for (int x = lo; x < hi; ++x) {
         const int ox = x - win.x1;
         bool on = false;
-        if constexpr (TILES_AA) {
+        if (aa_raster) {
           on = resized_mask_bit_aa(sm.cmask, aay, aax, y - win.y1, ox) || resized_mask_bit_aa(sm.bmask, aay, aax, y - win.y1, ox);
         } else {
           const int x0 = sm.tx0[ox], x1 = sm.tx1[ox];

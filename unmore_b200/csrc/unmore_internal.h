@@ -131,7 +131,9 @@ int launch_box_nms(const NmsParams& p, cudaStream_t stream);
 
 // ---- score.cu ------------------------------------------------------------------------
 struct ScoreParams {
-  const float* tiles;  // nullable: pre-resampled [n_img * cap, 4, 128, 128] (sdf, center_row, center_col, existence); selects the antialiased rasteriser
+  const float* tiles;  // nullable: pre-resampled [n_img * cap, 4, 128, 128] (sdf, center_row, center_col, existence)
+  const float* exist_scores;  // nullable, tile path only: [n_img, cap] per-crop existence scores instead of the mean of tile 3
+  int aa_raster;       // tile path only: resize the masks back to the box with the antialiased kernel
   const float* fields;
   int n_img, C, H, W, ch_sdf, ch_crow, ch_ccol, ch_exist;
   const void* boxes;   // [n_img, cap, 4]

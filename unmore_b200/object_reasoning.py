@@ -68,7 +68,7 @@ class FieldDataset:
 
 class Object_Discovery:
     def __init__(self, args: Optional[argparse.Namespace] = None, device=None, channels: ops.Channels = ops.DEFAULT_CHANNELS,
-                 test_dataset=None, result_folder: Optional[str] = None):
+                 test_dataset=None, result_folder: Optional[str] = None, tile_provider=None):
         """Reference: ``Object_Discovery(args, device)`` (object_reasoning.py:44-107).  The reference builds its
         nets and a COCO_Dataset from ``args``; here the producer is outside the path, so the dataset of field
         stacks (anything with ``__len__`` / ``get_image_with_index``, e.g. ``FieldDataset``) and the result
@@ -89,6 +89,9 @@ class Object_Discovery:
         # semantics (what the reference pins and the fused kernels implement), True = ATen's antialiased kernel
         # (torchvision >= 0.17's default).  args.antialias, when present, sets it.
         self.antialias = bool(getattr(self.args, "antialias", False))
+        # the reference's ORIGINAL mode: nets on every crop (producer.PerCropNets).  ``image`` is then the RGB image and
+        # every stage runs on the tiles the provider makes (the tile path), in the provider's resize mode.
+        self.tile_provider = tile_provider
 
     # ---- a1 ---------------------------------------------------------------------------
     @staticmethod
@@ -136,12 +139,26 @@ class Object_Discovery:
             proposals = proposals.to(torch.float64)
         return proposals.to(self.device).reshape(1, -1, 4).contiguous()
 
+    @property
+    def _tile_path(self) -> bool:
+        return self.antialias or self.tile_provider is not None
+
+    def _field_tiles(self, f: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        """[1,K,3,128,128] (sdf, center_row, center_col) tiles of ``boxes`` [1,K,4]: per-crop nets when a tile provider
+        is set, else antialiased crops of the per-image field stack."""
+        if self.tile_provider is not None:
+            return self.tile_provider.fields(f[0], boxes[0])[None]
+        ch = self.channels
+        return ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col], antialias=True)
+
     # ---- a3 ---------------------------------------------------------------------------
     def existence_checking(self, image, proposals) -> Dict[str, torch.Tensor]:
         """object_reasoning.py:491-523 — {'existence_scores': [N] fp32 on CPU}."""
         boxes = self._boxes(proposals)
         if boxes.shape[1] == 0:
             return {"existence_scores": torch.zeros((0,), dtype=torch.float32)}
+        if self.tile_provider is not None:   # the reference's original mode: one classifier output per crop
+            return {"existence_scores": self.tile_provider.existence(self._fields(image)[0], boxes[0]).cpu()}
         if self.antialias:   # tile path: antialiased crops of the existence channel, then their means
             tiles = ops.crop_resize(self._fields(image), boxes, [self.channels.exist], antialias=True)
             return {"existence_scores": ops.tile_means(tiles[0, :, 0]).cpu()}
@@ -154,7 +171,10 @@ class Object_Discovery:
         boundary-distance and center fields, (sdf_maps [N,128,128], center_fields [N,2,128,128])."""
         boxes = self._boxes(proposals)
         ch = self.channels
-        crops = ops.crop_resize(self._fields(image), boxes, [ch.sdf, ch.center_row, ch.center_col], antialias=self.antialias)[0]
+        if self.tile_provider is not None:
+            crops = self.tile_provider.fields(self._fields(image)[0], boxes[0])
+        else:
+            crops = ops.crop_resize(self._fields(image), boxes, [ch.sdf, ch.center_row, ch.center_col], antialias=self.antialias)[0]
         return crops[:, 0], crops[:, 1:3]
 
     # ---- a7 ---------------------------------------------------------------------------
@@ -166,10 +186,9 @@ class Object_Discovery:
             e = torch.zeros((0, 4), dtype=torch.float64, device=self.device)
             return {"proposals_pass_singularity": e, "splited_new_proposals": e.clone()}
         cc_on = bool(getattr(self.args, "analyze_cc", False))
-        if self.antialias:
+        if self._tile_path:
             f = self._fields(image)
-            ch = self.channels
-            tiles = ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col], antialias=True)
+            tiles = self._field_tiles(f, boxes)
             _, argmax, splits, cc = ops.center_reasoning_from_tiles(tiles, f.shape[-2], f.shape[-1], boxes,
                                                                     thr=self.args.center_score_max_thres, analyze_cc=cc_on)
         else:
@@ -194,7 +213,8 @@ class Object_Discovery:
         """Un-eroded union masks (object_reasoning.py:528-531) of ``boxes`` [1,K,4] as [K,128,128] u8, from the
         bit-exact resized crops and the same thresholds the center kernel applies (common.cuh)."""
         ch = self.channels
-        crops = ops.crop_resize(fields, boxes.contiguous(), [ch.sdf, ch.center_row, ch.center_col], antialias=self.antialias)[0]
+        crops = self._field_tiles(fields, boxes.contiguous())[0] if self.tile_provider is not None else \
+            ops.crop_resize(fields, boxes.contiguous(), [ch.sdf, ch.center_row, ch.center_col], antialias=self.antialias)[0]
         sq = crops[:, 1] * crops[:, 1] + crops[:, 2] * crops[:, 2]
         return ((crops[:, 0] > 8.94069671630859375e-08) | (sq > 0.2500000298023223876953125)).to(torch.uint8)
 
@@ -293,9 +313,9 @@ class Object_Discovery:
             return {"updated_bboxes": torch.zeros((0, 4), dtype=torch.float32, device=self.device),
                     "labels": torch.zeros((0,), dtype=torch.float32, device=self.device)}
         a = self.args
-        if self.antialias:
+        if self._tile_path:
             f = self._fields(image)
-            tiles = ops.crop_resize(f, boxes, [self.channels.sdf], antialias=True)[0, :, 0]
+            tiles = self._sdf_tiles(f, boxes[0])
             out, lab = ops.boundary_round_from_tiles(tiles, boxes[0], f.shape[-2], f.shape[-1], max_sdf_thres=a.max_sdf_thres,
                                                      max_shrink_threshold=a.max_shrink_threshold, delta_ratio=a.delta_ratio)
             return {"updated_bboxes": out, "labels": lab}
@@ -314,7 +334,7 @@ class Object_Discovery:
         if boxes.shape[1] == 0:
             return {"proposals": [], "labels": []}
         a = self.args
-        if self.antialias:
+        if self._tile_path:
             return self._boundary_reasoning_tiles(self._fields(image), boxes[0])
         out, lab, _ = ops.boundary_refine(self._fields(image), boxes, n_round=a.n_round, apply_small_filter=True,
                                           early_exit=True, proposal_area_thres=a.proposal_area_thres,
@@ -324,6 +344,12 @@ class Object_Discovery:
         if int(in_list.sum()) == 0:
             return {"proposals": [], "labels": []}
         return {"proposals": out[0][in_list], "labels": lab[0][in_list]}
+
+    def _sdf_tiles(self, f: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        """[K,128,128] boundary-distance tiles of ``boxes`` [K,4] on the tile path."""
+        if self.tile_provider is not None:
+            return self.tile_provider.fields(f[0], boxes)[:, 0].contiguous()
+        return ops.crop_resize(f, boxes[None].contiguous(), [self.channels.sdf], antialias=True)[0, :, 0]
 
     def _boundary_reasoning_tiles(self, f: torch.Tensor, cur: torch.Tensor):
         """boundary_reasoning (object_reasoning.py:582-612) in the second resize mode: the round loop runs on the
@@ -344,7 +370,7 @@ class Object_Discovery:
             newl = labels.clone()
             if bool(act.any()):
                 boxes = cur[act].contiguous()
-                tiles = ops.crop_resize(f, boxes[None].contiguous(), [self.channels.sdf], antialias=True)[0, :, 0]
+                tiles = self._sdf_tiles(f, boxes)
                 out, lab = ops.boundary_round_from_tiles(tiles, boxes, H, W, max_sdf_thres=a.max_sdf_thres,
                                                          max_shrink_threshold=a.max_shrink_threshold, delta_ratio=a.delta_ratio)
                 new[act] = out
@@ -366,7 +392,7 @@ class Object_Discovery:
         if proposals is None:
             proposals = self.generate_random_proposal(f.shape[-2], f.shape[-1])
         boxes = self._boxes(proposals)
-        if self.antialias:
+        if self._tile_path:
             return self._discover_image_tiles(f[0], boxes[0])
         det, cnt = self.discover_batch(f, boxes)
         return det[0, : int(cnt[0])].cpu().numpy()
@@ -414,7 +440,7 @@ class Object_Discovery:
         B, N = proposals.shape[0], proposals.shape[1]
         dev = fields.device
         f64 = torch.float64
-        if self.antialias:   # second resize mode: image by image on the tile path (not the batched fused kernels)
+        if self._tile_path:   # second resize mode / per-crop nets: image by image on the tile path (not the fused kernels)
             dets = [self._discover_image_tiles(fields[b], proposals[b] if counts is None else proposals[b, : int(counts[b])])
                     for b in range(B)]
             cap = max([len(d) for d in dets] + [1])

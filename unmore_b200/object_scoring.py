@@ -29,7 +29,8 @@ def unpack_masks(packed: torch.Tensor, width: int) -> np.ndarray:
 
 class Object_Scoring:
     def __init__(self, args: Optional[argparse.Namespace] = None, device=None, raw_annotations: Optional[dict] = None,
-                 channels: ops.Channels = ops.DEFAULT_CHANNELS, test_dataset=None, result_folder: Optional[str] = None):
+                 channels: ops.Channels = ops.DEFAULT_CHANNELS, test_dataset=None, result_folder: Optional[str] = None,
+                 tile_provider=None):
         """Reference: ``Object_Scoring(args, device)`` (object_scoring.py:45-104); dataset and result folder
         are handed in like in ``Object_Discovery``.  ``args.raw_annotations_path`` is read by
         ``load_raw_annotations`` when ``raw_annotations`` is not given."""
@@ -46,6 +47,7 @@ class Object_Scoring:
         self.result_folder = result_folder
         # resize mode (see Object_Discovery.antialias): True = the tile path with ATen's antialiased kernels
         self.antialias = bool(getattr(self.args, "antialias", False))
+        self.tile_provider = tile_provider   # producer.PerCropNets: the reference's original per-crop mode (image = RGB)
         if raw_annotations is None and getattr(self.args, "raw_annotations_path", None):
             self.load_raw_annotations()
 
@@ -66,6 +68,9 @@ class Object_Scoring:
         boxes = torch.as_tensor(np.asarray(proposals, dtype=np.float64)).reshape(1, -1, 4).to(self.device)
         ch = self.channels
         f = self._fields(image)
+        if self.tile_provider is not None:
+            return {"pred_boundary_fields": (t := self.tile_provider.fields(f[0], boxes[0]))[:, 0], "pred_center_fields": t[:, 1:3],
+                    "pred_existence_scores": self.tile_provider.existence(f[0], boxes[0])}
         if self.antialias:
             crops = ops.crop_resize(f, boxes, [ch.sdf, ch.center_row, ch.center_col, ch.exist], antialias=True)[0]
             return {"pred_boundary_fields": crops[:, 0], "pred_center_fields": crops[:, 1:3],
@@ -80,7 +85,19 @@ class Object_Scoring:
         order: out [B,cap,5] fp64 (score, existence, center, boundary, area_score), bbox [B,cap,4] xywh,
         selected [B,cap] (post_process predicate), keep [B,cap], keep_counts [B], masks (packed, indexed by
         the ORIGINAL proposal index: use keep to gather)."""
-        if self.antialias:
+        if self.tile_provider is not None:   # per-crop nets: (sdf, center) tiles + one classifier scalar per crop
+            B, cap = boxes.shape[0], boxes.shape[1]
+            tiles = torch.zeros((B, cap, 4, ops.CROP, ops.CROP), dtype=torch.float32, device=fields.device)
+            ex = torch.zeros((B, cap), dtype=torch.float32, device=fields.device)
+            for b in range(B):
+                n = cap if counts is None else int(counts[b])
+                if n:
+                    tiles[b, :n, 0:3] = self.tile_provider.fields(fields[b], boxes[b, :n])
+                    ex[b, :n] = self.tile_provider.existence(fields[b], boxes[b, :n])
+            scores, tight, areas, masks = ops.score_and_rasterise_from_tiles(
+                tiles, fields.shape[-2], fields.shape[-1], boxes, counts, want_masks=want_masks,
+                antialias=self.tile_provider.antialias, existence_scores=ex)
+        elif self.antialias:
             ch = self.channels
             tiles = ops.crop_resize(fields, boxes, [ch.sdf, ch.center_row, ch.center_col, ch.exist], counts, antialias=True)
             scores, tight, areas, masks = ops.score_and_rasterise_from_tiles(tiles, fields.shape[-2], fields.shape[-1], boxes, counts,

@@ -542,9 +542,11 @@ def boundary_round_from_tiles(tiles, boxes, H, W, max_sdf_thres: float = 0.5, ma
     return out, lab
 
 
-def score_and_rasterise_from_tiles(tiles, H, W, boxes, counts=None, want_masks: bool = True):
+def score_and_rasterise_from_tiles(tiles, H, W, boxes, counts=None, want_masks: bool = True, antialias: bool = True,
+                                   existence_scores: Optional[torch.Tensor] = None):
     """score_and_rasterise on tiles [n_img, cap, 4, 128, 128] = (sdf, center_row, center_col, existence); the masks are
-    resized back to the box with the ANTIALIASED kernel.  Same returns as ``score_and_rasterise``."""
+    resized back to the box with the antialiased kernel (``antialias``) or the plain one; ``existence_scores``
+    [n_img, cap] fp32, when given, replaces the mean of the fourth tile.  Same returns as ``score_and_rasterise``."""
     tiles = _on(tiles.contiguous())
     n_img, cap = tiles.shape[0], tiles.shape[1]
     _, f64 = _check_boxes(boxes, n_img)
@@ -556,6 +558,9 @@ def score_and_rasterise_from_tiles(tiles, H, W, boxes, counts=None, want_masks: 
     masks = torch.zeros((n_img, cap, H, (W + 31) // 32), dtype=torch.int32, device=dev) if want_masks else None
     _on(tiles)
     if cap > 0:
-        _call("unmore_score_and_rasterise_from_tiles", tiles.data_ptr(), n_img, int(H), int(W), boxes.data_ptr(), f64, _ptr(counts), cap,
+        if existence_scores is not None:
+            existence_scores = existence_scores.to(dev, torch.float32).reshape(n_img, cap).contiguous()
+        _call("unmore_score_and_rasterise_from_tiles", tiles.data_ptr(), _ptr(existence_scores), int(antialias), n_img, int(H), int(W),
+              boxes.data_ptr(), f64, _ptr(counts), cap,
               scores.data_ptr(), tight.data_ptr(), areas.data_ptr(), _ptr(masks), _stream())
     return scores, tight, areas, masks

@@ -376,3 +376,47 @@ class FieldProducer(nn.Module):
         if s > 0:
             h.weight.mul_(exist_logit_std / s)
             h.bias.fill_(float(-(y * (exist_logit_std / s)).mean()) + 0.5)   # centred, slightly positive
+
+
+class PerCropNets:
+    """The reference's ORIGINAL mode: the nets run on every 128x128 crop of the RGB image, every time a stage needs
+    them (object_reasoning.py:311-333, 398-417, 496-512; object_scoring.py:112-157) — instead of once per image.
+
+    A *tile provider* for ``Object_Discovery`` / ``Object_Scoring`` (``tile_provider=PerCropNets(...)``): the Python
+    loop of per-box ``image[:, y1:y2, x1:x2]`` + ``Resize`` + four device->host syncs per box becomes ONE batched
+    ``unmore_crop_resize`` (either resize mode) of all boxes, the crops go through the nets in batches (50 / 128 like
+    the reference), and the reasoning stages consume the resulting tiles on the device (the ``*_from_tiles`` C-ABI
+    entry points).  ``image`` is then the RGB image [3, H, W], exactly as in the reference."""
+
+    def __init__(self, objectness_model: nn.Module, binary_classifier_model: nn.Module, antialias: bool = False,
+                 objectness_batch: int = 50, classifier_batch: int = 128):
+        self.objectness_model = objectness_model.eval()
+        self.binary_classifier_model = binary_classifier_model.eval()
+        self.antialias = antialias
+        self.objectness_batch = objectness_batch
+        self.classifier_batch = classifier_batch
+
+    def crops(self, image: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        """[3,H,W] image + [N,4] boxes -> [N,3,128,128] crops (a2, batched on the device)."""
+        from . import ops
+        img = image.to(torch.float32)
+        return ops.crop_resize(img[None].contiguous(), boxes.reshape(1, -1, 4).contiguous(), [0, 1, 2], antialias=self.antialias)[0]
+
+    @torch.no_grad()
+    def fields(self, image: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        """-> [N,3,128,128] = (sdf, center_row, center_col) tiles of every box (get_prediction_with_proposals)."""
+        crops = self.crops(image, boxes)
+        out = torch.empty((crops.shape[0], 3, crops.shape[2], crops.shape[3]), dtype=torch.float32, device=crops.device)
+        for b0 in range(0, crops.shape[0], self.objectness_batch):
+            pred = self.objectness_model(crops[b0:b0 + self.objectness_batch])
+            out[b0:b0 + self.objectness_batch, 0:1] = pred["sdf_maps"]
+            out[b0:b0 + self.objectness_batch, 1:3] = pred["center_fields"]
+        return out
+
+    @torch.no_grad()
+    def existence(self, image: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+        """-> [N] existence scores, one classifier output per crop (existence_checking)."""
+        crops = self.crops(image, boxes)
+        out = [self.binary_classifier_model(crops[b0:b0 + self.classifier_batch]).reshape(-1)
+               for b0 in range(0, crops.shape[0], self.classifier_batch)]
+        return torch.cat(out) if out else torch.zeros((0,), dtype=torch.float32, device=crops.device)
