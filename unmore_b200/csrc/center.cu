@@ -179,6 +179,35 @@ struct CenterRows {
     for (int c = 0; c < 4; ++c)
       cc[c] = lerp_h2(pk2(v0[1][c], v0[2][c]), pk2(v1[1][c], v1[2][c]), pk2(w0[c], w0[c]), pk2(w1[c], w1[c]));
   }
+  // L1 prefetch of the source rows the NEXT output row will need and the cache does not hold (no registers, no
+  // scoreboard): stage 1 is latency-bound (4 warps per sub-partition, 24 dependent taps per new source row), so the
+  // L2 round trip of the next row is started one output row early.  One prefetch per column and plane: the right tap
+  // shares the sector of the left one in all but 1 of 8 positions.
+  __device__ __forceinline__ void prefetch_next(const ColTaps& t, const AxisTap& v) const {
+#ifdef UNMORE_CENTER_PREFETCH
+    auto pf = [&](int y) {
+      const int ro = y * stride;
+      if constexpr (PLANE_ELEMS > 0) {
+        const float* rowp = elem_ptr(origin[0], ro);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float* a0 = byte_ptr(rowp, t.x0[c]);
+#pragma unroll
+          for (int p = 0; p < 3; ++p) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + p * PLANE_ELEMS));
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const float* rowp = elem_ptr(origin[p], ro);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) asm volatile("prefetch.global.L1 [%0];" ::"l"(byte_ptr(rowp, t.x0[c])));
+        }
+      }
+    };
+    if (v.i0 != cy0 && v.i0 != cy1) pf(v.i0);
+    if (v.i1 != v.i0 && v.i1 != cy1 && v.i1 != cy0) pf(v.i1);
+#endif
+  }
   // s[c] = sdf of column lane + 32c; ab[c] = (c_row, c_col) of that column
   __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float s[4], f32x2 ab[4]) {
     if (v.i0 != cy0 || v.i1 != cy1) {          // warp-uniform
@@ -313,7 +342,10 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         float s[4];
         f32x2 ab[4];
         if constexpr (PLANE_ELEMS < 0) trows.row(lane, i, s, ab);
-        else rows.row(taps, v, s, ab);
+        else {
+          rows.row(taps, v, s, ab);
+          if (i + 1 < row_hi) rows.prefetch_next(taps, axis_tap(scale_y, i + 1, in_h));
+        }
         uint32_t word[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -340,6 +372,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       if (lane == 0) sm.red_f[warp] = cabs;
       __syncthreads();
       locate_next();
+#ifndef UNMORE_CENTER_SKIP_S23   // timing-only builds: profiles/r02_center_phase_times.md
       // ---- 2. erosion: 25-runs along rows, then AND of 25 rows
       if (tid == kCrop) sm.cand_n = 0;   // an idle thread of this phase; ordered by the barriers around it
       if (tid < kCrop) {
@@ -359,6 +392,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         store_row(sm.ero[tid], e);
       }
       __syncthreads();
+#ifndef UNMORE_CENTER_SKIP_S3
       // ---- 3. anti-center map on surviving pixels, then masked max / first arg-max.
       // The map is needed in fp64 only where it can decide the result (the maximum).  So: (a) an
       // fp32 register-tiled 5x5x2 correlation over 1x8 pixel strips that contain surviving pixels
@@ -524,6 +558,8 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         }
         best = ov; best_idx = oi;
       }
+#endif
+#endif
     }
     if (tid == 0) {
       // amax over the whole map: pixels outside the eroded mask contribute 0
