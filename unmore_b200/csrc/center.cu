@@ -336,9 +336,22 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       unsigned stage_addr = smem_addr(&sm.c[0]) + (unsigned)(((row_lo - kWinLo) * kWinStride + (lane - kWinLo)) * 8);
       unsigned mask_addr = smem_addr(&sm.mask[0][0]) + 16u * (unsigned)row_lo;
       const bool lane0 = lane == 0;
+      // the vertical taps of the warp's rows are computed ONCE, one row per lane, and handed out by shuffle: the
+      // I2F / FFMA / F2I / I2F chain of axis_tap no longer sits in front of every row's loads
+#ifndef UNMORE_CENTER_NO_TAP_SHFL
+      const AxisTap my_tap = axis_tap(scale_y, min(row_lo + lane % kRowsPerWarp, kCrop - 1), in_h);
+#endif
       for (int i = row_lo; i < row_hi; ++i, stage_addr += kWinStride * 8, mask_addr += 16) {
         const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
+#ifndef UNMORE_CENTER_NO_TAP_SHFL
+        AxisTap v;
+        v.i0 = __shfl_sync(kFullMask, my_tap.i0, i - row_lo);
+        v.l1 = __shfl_sync(kFullMask, my_tap.l1, i - row_lo);
+        v.i1 = min(v.i0 + 1, in_h - 1);
+        v.l0 = __fsub_rn(1.f, v.l1);
+#else
         const AxisTap v = axis_tap(scale_y, i, in_h);
+#endif
         float s[4];
         f32x2 ab[4];
         if constexpr (PLANE_ELEMS < 0) trows.row(lane, i, s, ab);
@@ -357,7 +370,11 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
           const float sq = __fadd_rn(a2, b2);
           const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
           word[c] = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
+#ifdef UNMORE_CENTER_CABS_EXACT
           cabs = fmaxf(cabs, fmaxf(fabsf(a), fabsf(b)));
+#else
+          cabs = fmaxf(cabs, sq);   // max of the squared norms: sqrt of it bounds max(|a|, |b|) (one instruction instead of three)
+#endif
         }
         st_shared_b32_if<0>(lane0, mask_addr, word[0]);
         st_shared_b32_if<4>(lane0, mask_addr, word[1]);
@@ -369,6 +386,9 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
         st_shared_b64_if<768>(row_in && col_in[3], stage_addr, ab[3]);
       }
       cabs = warp_max(cabs);
+#ifndef UNMORE_CENTER_CABS_EXACT
+      cabs = __fmul_rn(__fsqrt_ru(cabs), 1.000001f);   // an upper bound of max |center field| is all the margin needs
+#endif
       if (lane == 0) sm.red_f[warp] = cabs;
       __syncthreads();
       locate_next();
