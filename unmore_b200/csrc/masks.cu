@@ -28,8 +28,15 @@ __device__ __forceinline__ uint32_t nz4(uint32_t w) {
 // fast path: W % 32 == 0.  A lane loads 16 pixels (one uint4), pairs of lanes form a word.  Persistent grid-stride loop:
 // every thread keeps kPackUnroll independent 16-byte loads in flight and requests the NEXT batch before it packs the
 // current one, so the HBM pipe never drains between batches and there is no per-CTA launch / drain overhead (the
-// one-shot form reached 0.57 / 0.74 / 0.80 of the measured copy bandwidth at 1k / 4k / 16k masks).
-constexpr int kPackUnroll = 4;
+// one-shot form reached 0.57 / 0.74 / 0.80 of the measured copy bandwidth at 1k / 4k / 16k masks; this form with 4
+// resident CTAs per SM: 0.79 / 0.88 / 0.94, where a plain device copy of the same bytes reaches 0.84 / 0.96 / 0.99).
+#ifndef UNMORE_PACK_UNROLL
+#define UNMORE_PACK_UNROLL 4
+#endif
+#ifndef UNMORE_PACK_CTAS_PER_SM
+#define UNMORE_PACK_CTAS_PER_SM 4   // measured: 2 / 3 / 4 / 5 / 8 CTAs per SM -> 0.82 / 0.92 / 0.94 / 0.91 / 0.87 of the copy bandwidth at 16k masks
+#endif
+constexpr int kPackUnroll = UNMORE_PACK_UNROLL;
 __global__ void __launch_bounds__(256) pack_kernel_vec(const uint4* __restrict__ in, uint32_t* __restrict__ out,
                                                        size_t n_vec) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;   // even: lane pairs stay together in every batch
@@ -78,7 +85,7 @@ int launch_mask_pack(const unsigned char* in, uint32_t* out, size_t n_masks, int
     const size_t n_vec = n_masks * H * (size_t)W / 16;
     const size_t per_block = 256 * (size_t)kPackUnroll;   // n_vec is even (W % 32 == 0), so lane pairs never straddle strides
     const size_t want = (n_vec + per_block - 1) / per_block;
-    const size_t resident = (size_t)num_sms * 8;           // 8 CTAs of 256 threads fill an SM
+    const size_t resident = (size_t)num_sms * UNMORE_PACK_CTAS_PER_SM;
     pack_kernel_vec<<<(unsigned)(want < resident ? want : resident), 256, 0, stream>>>(reinterpret_cast<const uint4*>(in), out, n_vec);
   } else {
     const size_t total = n_masks * H * (size_t)Wp;
