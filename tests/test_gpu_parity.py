@@ -868,3 +868,46 @@ def test_antialias_scene_scoring(golden_dir, dev):
     masks = np.stack([a["segmentation"]["mask"] for a in anns])
     packed = np.packbits(masks.reshape(len(anns), -1), axis=1, bitorder="little")
     assert np.array_equal(packed, g["score_masks_packed"]), "binary masks must be bit-exact (antialias)"
+
+
+def test_antialias_crops_extreme_windows_vs_oracle(dev, ops):
+    """Antialiased a2 on windows the goldens do not hold: 1x1, 2x3, a 1-pixel-wide strip, and a 1000x1000 window of a
+    1024x1024 field (16-17 taps per axis) — against the pinned numpy restatement (oracle.resize_bilinear_aa_np)."""
+    g = torch.Generator().manual_seed(11)
+    f = torch.randn((1, 2, 1024, 1024), generator=g)
+    boxes = np.array([[10.0, 20.0, 11.0, 21.0], [100.2, 200.7, 101.9, 203.1], [5.0, 5.0, 6.0, 400.0],
+                      [12.3, 7.9, 1011.5, 1007.2], [0.0, 0.0, 1024.0, 1024.0], [500.0, 500.0, 628.0, 628.0]])
+    got = ops.crop_resize(f.to(dev), torch.tensor(boxes, device=dev)[None].contiguous(), [0, 1], antialias=True)[0].cpu().numpy()
+    for k, b in enumerate(boxes):
+        x1, y1, x2, y2 = O.snap_box(b)
+        for c in range(2):
+            ref = O.resize_bilinear_aa_np(f[0, c, y1:y2, x1:x2].numpy(), 128, 128)
+            assert np.array_equal(got[k, c], ref), (k, c, float(np.abs(got[k, c] - ref).max()))
+
+
+def test_pack_detections_rows_edge_cases(dev, ops):
+    """unmore_pack_detections: append across batches, empty images, image ids beyond 2^24, capacity overflow flag."""
+    from unmore_b200.sharding import merge_rows
+    cap = 4
+    ids = torch.tensor([2 ** 40 + 7, 3, 2 ** 33], dtype=torch.int64, device=dev)
+    bbox = torch.arange(3 * cap * 4, dtype=torch.float32, device=dev).reshape(3, cap, 4).contiguous()
+    out5 = torch.arange(3 * cap * 5, dtype=torch.float64, device=dev).reshape(3, cap, 5).contiguous() / 7
+    kc = torch.tensor([2, 0, 4], dtype=torch.int32, device=dev)
+    rows = ops.detection_rows(16, dev)
+    ops.pack_detections(ids, bbox, out5, kc, rows)
+    ops.pack_detections(ids[:1], bbox[:1], out5[:1], kc[:1], rows)          # second batch appends
+    r = rows.cpu().numpy()
+    assert r[0, 0] == 8 and r[0, 1] == 0
+    exp_img = [2 ** 40 + 7] * 2 + [2 ** 33] * 4 + [2 ** 40 + 7] * 2
+    assert r[1:9, 0].tolist() == [float(v) for v in exp_img]
+    assert np.array_equal(r[1:3, 1:5], bbox[0, :2].cpu().numpy()) and np.array_equal(r[3:7, 1:5], bbox[2].cpu().numpy())
+    assert np.array_equal(r[1:3, 5], out5[0, :2, 0].cpu().numpy())
+    merged, total = merge_rows(rows[None])
+    assert int(total) == 8 and merged[:8, 0].cpu().tolist() == sorted(float(v) for v in exp_img)
+    small = ops.detection_rows(3, dev)
+    ops.pack_detections(ids, bbox, out5, kc, small)
+    s = small.cpu().numpy()
+    assert s[0, 0] == 3 and s[0, 1] == 1                                     # clamped + overflow flag
+    empty = ops.detection_rows(4, dev)
+    ops.pack_detections(ids, bbox, out5, torch.zeros(3, dtype=torch.int32, device=dev), empty)
+    assert float(empty[0, 0]) == 0
