@@ -5,6 +5,7 @@
     python bench.py --impl reference ...                          # the CPU oracle port, bounded sample
     python bench.py --scaling strong ...                          # 5000 images TOTAL, interleaved over the ranks
     python bench.py --config producer [--producer-dtype fp32]     # configs[4]: DPT-L producer -> reasoning, 1024x1024
+    python bench.py --config antialias [--images 16]              # the second resize mode (tile path), image by image
 
 configs[1] (default): a COCO-val-shaped synthetic batch — 5000 images of 480x640 fields, 4096 proposals per
 image — through discovery (existence check, center reasoning, iterative boundary refinement, NMS), scoring +
@@ -38,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="reasoning", choices=["reasoning", "producer"])
+    ap.add_argument("--config", default="reasoning", choices=["reasoning", "producer", "antialias"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--images", type=int, default=None, help="images per rank (weak) or in total (strong); default 5000 (reasoning) / 16 (producer)")
     ap.add_argument("--proposals", type=int, default=N_PROP)
@@ -197,10 +198,57 @@ def parity_sample(pipe, dev, oracle_res):
 
 
 # ---------------------------------------------------------------------------------------------
+def run_antialias(args):
+    """The second resize mode (antialias=True, tile path) on a few benchmark images, image by image through the mirror
+    classes: a labelled side figure, not the headline (the fused kernels implement the pinned antialias=False)."""
+    import argparse as ap_
+    import numpy as np
+    import torch
+    from unmore_b200 import ops, synth
+    from unmore_b200.object_reasoning import Object_Discovery, default_args
+    from unmore_b200.object_scoring import Object_Scoring
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    n_img = args.images or 16
+    od = Object_Discovery(default_args(antialias=True), device=dev)
+    sc = Object_Scoring(ap_.Namespace(antialias=True), device=dev)
+    imgs = [synth.make_fields(i, H, W).to(dev) for i in range(n_img)]
+    props = [synth.make_proposals(i, args.proposals, H, W) for i in range(n_img)]
+
+    def step():
+        n = 0
+        for f, p in zip(imgs, props):
+            det = od.discover_image(f, p)
+            if len(det):
+                n += len(sc.score_image(f, det.astype(np.float64).tolist()))
+        return n
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    torch.cuda.synchronize()
+    l0 = ops.LAUNCHES
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_ann = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    print(json.dumps({"metric": "object_reasoning_images_per_sec", "value": n_img / dt, "unit": "images/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"second resize mode (antialias=True, tile path, image by image): {n_img} synthetic 480x640 "
+                                             f"field stacks x {args.proposals} proposals, discovery + scoring through the mirror classes",
+                                 "resize": "bilinear, antialias=True (torchvision >= 0.17 default)"},
+                      "annotations": n_ann, "gpu_launches": ops.LAUNCHES - l0, "timing": "wall clock around synchronised steps"}))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "antialias":
+        return run_antialias(args)
 
     import numpy as np
     import torch

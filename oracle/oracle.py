@@ -37,6 +37,25 @@ import torch
 import torch.nn.functional as F
 
 CROP = 128  # hard-coded crop side, object_reasoning.py:319,407,505
+ANTIALIAS = False  # resize mode of every transforms.Resize call of the path: False = torchvision 0.14.1 (pinned), True = >= 0.17 default
+
+
+class antialias_mode:
+    """``with oracle.antialias_mode(True): ...`` runs the oracle in the second resize mode (both Resize sites: the crops
+    and the int-mask resize back to the box)."""
+
+    def __init__(self, on: bool):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global ANTIALIAS
+        self.prev, ANTIALIAS = ANTIALIAS, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global ANTIALIAS
+        ANTIALIAS = self.prev
+        return False
 
 DEFAULTS = dict(class_score_thres=0.1, center_score_max_thres=0.009, analyze_cc=False,
                 max_sdf_thres=0.5, max_shrink_threshold=16, delta_ratio=0.5, n_round=50,
@@ -65,7 +84,7 @@ def crop_resize(image: torch.Tensor, box, size=(CROP, CROP)) -> torch.Tensor:
     x1, y1, x2, y2 = snap_box(box)
     crop = image[:, y1:y2, x1:x2]
     return F.interpolate(crop.unsqueeze(0), size=list(size), mode="bilinear", align_corners=False,
-                         antialias=False)[0]
+                         antialias=ANTIALIAS)[0]
 
 
 def on_edge_flags(box, height, width) -> np.ndarray:
@@ -566,7 +585,7 @@ def resize_mask_to_box(mask128: torch.Tensor, out_h: int, out_w: int) -> torch.T
     """int64 {0,1} [128,128] -> Resize((h,w), BILINEAR) as torchvision does for integer
     tensors: cast to float32, interpolate, torch.round (half to even), cast back."""
     f = F.interpolate(mask128.to(torch.float32)[None, None], size=[out_h, out_w], mode="bilinear",
-                      align_corners=False, antialias=False)[0, 0]
+                      align_corners=False, antialias=ANTIALIAS)[0, 0]
     return torch.round(f).to(torch.int64)
 
 

@@ -911,3 +911,28 @@ def test_pack_detections_rows_edge_cases(dev, ops):
     empty = ops.detection_rows(4, dev)
     ops.pack_detections(ids, bbox, out5, torch.zeros(3, dtype=torch.int32, device=dev), empty)
     assert float(empty[0, 0]) == 0
+
+
+def test_antialias_fuzz_vs_oracle(dev, oda):
+    """Seeded scenes in the second resize mode (tile path) against the oracle run with antialias_mode(True) — the
+    oracle is pinned in that mode by the reference-run golden (tests/test_oracle_golden.py)."""
+    import argparse
+    from unmore_b200.object_scoring import Object_Scoring
+    sc = Object_Scoring(argparse.Namespace(antialias=True), device=dev)
+    args = O.make_args()
+    n_det = 0
+    for s in range(4000, 4006):
+        img = synth.make_fields(s)
+        props = synth.make_proposals(s, 120)
+        with O.antialias_mode(True):
+            ref = O.discover_image(img, props, args)
+            s_ref = O.score_image(img, ref.tolist(), args) if len(ref) else None
+        det = oda.discover_image(img.to(dev), props)
+        assert_boxes_close(det, ref, f"seed {s} (antialias)")
+        n_det += len(ref)
+        if len(ref):
+            anns = sc.score_image(img.to(dev), ref.astype(np.float64).tolist())
+            assert len(anns) == len(s_ref["score"]), s
+            assert np.array_equal(np.stack([a["segmentation"]["mask"] for a in anns]), s_ref["masks"]), s
+            assert_rel([a["score"] for a in anns], s_ref["score"], f"score, seed {s} (antialias)")
+    assert n_det > 0

@@ -223,3 +223,24 @@ def test_antialias_resize_bit_exact():
         f = F.interpolate(m[None, None].float(), size=(oh, ow), mode="bilinear", align_corners=False, antialias=True)[0, 0]
         got = np.round(O.resize_bilinear_aa_np(m.numpy().astype(np.float32), oh, ow))
         assert np.array_equal(got, torch.round(f).numpy()), (oh, ow)
+
+
+def test_oracle_antialias_mode_reproduces_the_reference_run(golden_dir):
+    """The oracle with ``antialias_mode(True)`` (both Resize sites) against the goldens of the reference run with
+    torchvision's current default (scene_aa.npz): stage lists, discovery output, scoring boxes and masks."""
+    g = _load(golden_dir, "scene_aa.npz")
+    idx = int(g["index"])
+    img = synth.make_fields(idx)
+    props = synth.make_proposals(idx, int(g["n_prop"]))
+    args = O.make_args()
+    with O.antialias_mode(True):
+        dbg = {}
+        det = O.discover_image(img, props, args, debug=dbg)
+        sc = O.score_image(img, g["discovered"].astype(np.float64).tolist(), args)
+    assert O.ANTIALIAS is False
+    assert np.array_equal(dbg["existence_scores"].numpy(), g["existence_scores"])
+    assert np.array_equal(dbg["pass1"].numpy(), g["pass1"]) and np.array_equal(dbg["refine_in"].numpy(), g["refine_in"])
+    assert np.array_equal(det, g["discovered"])
+    assert np.array_equal(sc["bbox"], g["score_bbox"])
+    assert np.array_equal(np.packbits(sc["masks"].reshape(len(sc["score"]), -1), axis=1, bitorder="little"), g["score_masks_packed"])
+    assert np.allclose(sc["score"], g["score_score"], rtol=1e-12, atol=0)
