@@ -4,6 +4,7 @@ PyTorch is only the allocator / stream provider here; all arithmetic runs in
 ``libunmore_b200.so``.  Inputs must be CUDA tensors; there is no CPU path."""
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -26,20 +27,23 @@ class Channels:
 DEFAULT_CHANNELS = Channels()
 
 
-_device = None   # device of the call being assembled: set by _on(), consumed by _stream() / _call()
+_tls = threading.local()   # .device = device of the call being assembled on THIS thread: set by _on(), consumed by _stream() / _call()
 
 
 def _on(t: torch.Tensor):
     """Pins the device of the call being assembled to the device of its first tensor (the C ABI
     launches on the CURRENT device; without this, tensors on cuda:1 under a current device of cuda:0 would be
-    dereferenced by a kernel running on GPU 0)."""
-    global _device
-    _device = t.device
+    dereferenced by a kernel running on GPU 0).  Per thread, like the library's error string."""
+    _tls.device = t.device
     return t
 
 
+def _cur_device():
+    return getattr(_tls, "device", None)
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream(_device).cuda_stream
+    return torch.cuda.current_stream(_cur_device()).cuda_stream
 
 
 class StageTimer:
@@ -51,7 +55,7 @@ class StageTimer:
         self.launches = 0
 
     def record(self, name, kernels, fn, *args):
-        st = torch.cuda.current_stream(_device)
+        st = torch.cuda.current_stream(_cur_device())
         a = torch.cuda.Event(enable_timing=True)
         b = torch.cuda.Event(enable_timing=True)
         a.record(st)
@@ -89,10 +93,10 @@ def set_timer(t: Optional[StageTimer]):
 
 
 def _call(name, *args, counts=None):
-    global LAUNCHES, _device
+    global LAUNCHES
     k = _KERNELS[name] + (1 if counts is not None else 0)
     LAUNCHES += k
-    dev = _device
+    dev = _cur_device()
     try:
         if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
             with torch.cuda.device(dev):
@@ -102,7 +106,7 @@ def _call(name, *args, counts=None):
         else:
             _lib.call(name, *args)
     finally:
-        _device = None
+        _tls.device = None
 
 
 def _ptr(t: Optional[torch.Tensor]):
