@@ -17,5 +17,6 @@ for LIB in "$@"; do
   else
     UNMORE_B200_LIB=$LIB KB_CMP=gpurun_out/kb_ref.pt python scripts/kbench.py $NI "${KS[@]}" > gpurun_out/ab_$tag.log 2>&1
   fi
-  echo "== $tag (rc=$?)"; grep -E "^(exist|center|refine|score|sat|pack) |vs saved|Error|error" gpurun_out/ab_$tag.log
+  echo "== $tag (rc=$?)"; grep -E "^(exist|center|center2|refine|score|sat|pack) +:|vs saved|Error|error" gpurun_out/ab_$tag.log
 done
+rm -f gpurun_out/kb_ref.pt*   # large; only needed between the builds of one call

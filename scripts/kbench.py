@@ -48,6 +48,11 @@ if which & {"all", "center"}:
     if os.environ.get("KB_CMP") and os.path.exists(os.environ["KB_CMP"] + ".center"):
         ref = torch.load(os.environ["KB_CMP"] + ".center")
         print("   vs saved: center outputs bit-equal", all(bool(torch.equal(ref[k], co[k])) for k in co))
+if which & {"all", "center"}:   # second pass: the split proposals that survive the existence re-check
+    p2, c2 = st["pass2_boxes"], st["pass2"]
+    n2 = int(c2.sum())
+    mn, av = timeit(lambda: ops.center_reasoning(fields, p2, c2, ws=ws, want_splits=False))
+    print(f"center2 : {mn:8.3f} ms min {av:8.3f} avg  {n2/mn/1e3:8.2f} Mprop/s  ({n2} split proposals)")
 if which & {"all", "refine"}:
     rin, rc = st["refine_in_boxes"], st["refine_in"]
     rounds = int(st["refine_rounds"].sum())

@@ -193,6 +193,49 @@ def test_center_reasoning_plateaus_and_ties(od, dev, ops):
     assert len(O.center_reasoning(cases[1][1], props, args)["splited_new_proposals"]) > 0   # the seam case does split
 
 
+def test_center_reasoning_survivor_bands_vs_oracle(od, dev, ops):
+    """The center kernel resamples only the rows that can hold survivors of the 25x25 erosion (decided from eight
+    lattice rows).  Union masks made of rectangles whose edges sweep across the lattice rows, the 12-pixel erosion
+    frame and the 25-pixel run length — one or two bands per 128x128 crop, crops taken 1:1 and scaled — must give the
+    reference's maxima (1e-14: fp64 summation order) and exactly the same pass / split lists."""
+    H, W = 480, 640
+    rng = np.random.default_rng(314)
+    args = O.make_args()
+    edges = [0, 1, 3, 4, 7, 8, 9, 11, 12, 13, 19, 20, 21, 24, 36, 37]
+    sizes = [23, 24, 25, 26, 27, 33, 40, 41, 49, 57, 64, 90, 128]
+    for img in range(6):
+        f = torch.zeros((4, H, W))
+        f[0] = -1.0; f[3] = 1.0
+        f[1:3] = torch.tensor(rng.normal(0, 0.12, (2, H, W)).astype(np.float32))
+        props = []
+        for cy in range(3):
+            for cx in range(5):
+                oy, ox = 128 * cy + (32 if cy else 0), 128 * cx
+                for _ in range(int(rng.integers(1, 3))):          # one or two rectangles in the cell
+                    a, c = int(rng.choice(edges)), int(rng.choice(edges))
+                    if rng.random() < 0.4:
+                        a = 127 - a - int(rng.choice(sizes[:6]))  # hug the bottom edge instead
+                    h, w = int(rng.choice(sizes)), int(rng.choice(sizes))
+                    a = max(a, 0)
+                    f[0, oy + a: min(oy + a + h, oy + 128), ox + c: min(ox + c + w, ox + 128)] = 1.0
+                props.append([ox, oy, ox + 128, oy + 128])                      # 1:1 crop
+                props.append([ox + 3, oy + 5, ox + 128 - 9, oy + 128 - 2])      # scaled crop of the same content
+        props = torch.tensor(props, dtype=torch.float64)
+        props[:, [1, 3]] = props[:, [1, 3]].clamp(0, H)
+        ref = O.center_reasoning(f, props, args, return_debug=True)
+        got = od.center_reasoning(f.to(dev), props)
+        assert np.array_equal(got["proposals_pass_singularity"].cpu().numpy(), ref["proposals_pass_singularity"].numpy()), img
+        assert np.array_equal(got["splited_new_proposals"].cpu().numpy().reshape(-1, 4),
+                              ref["splited_new_proposals"].numpy().reshape(-1, 4)), img
+        mv = ops.center_reasoning(f.to(dev)[None].contiguous(), props.to(dev)[None].contiguous())[0]
+        got_mv, ref_mv = mv[0].cpu().numpy(), ref["max_values"].numpy()
+        # the fp64 correlation is a library convolution in the reference (summation order unspecified): 1e-14, as
+        # test_batch_erode_and_anti_center; "no survivor" (exactly 0) must agree exactly
+        assert np.array_equal(got_mv == 0, ref_mv == 0) and np.allclose(got_mv, ref_mv, rtol=0, atol=1e-14), img
+        n_empty = int((ref["eroded"].reshape(len(props), -1).sum(1) == 0).sum())
+        assert 0 < n_empty < len(props)        # both the early exit and the partial pass are exercised
+
+
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_scene_single_rounds_teacher_forced(golden_dir, od, dev, tag):
     """optimize_one_image_single_round with inputs forced from the reference's own trajectory:

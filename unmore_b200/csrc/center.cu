@@ -15,6 +15,9 @@
 
 namespace unmore {
 
+#ifndef UNMORE_CENTER_LATTICE
+#define UNMORE_CENTER_LATTICE 1   // 0: resample all 128 rows of every proposal (the round-1 schedule); 2: timing-only, pre-pass without skipping
+#endif
 #ifndef UNMORE_CENTER_THREADS
 #define UNMORE_CENTER_THREADS 256
 #endif
@@ -143,9 +146,9 @@ struct CenterRows {
     stride = W;
     cy0 = cy1 = -1;
   }
-  __device__ __forceinline__ void hrows(const ColTaps& t, int y, f32x2 s[2], f32x2 cc[4]) const {
+  // the 24 taps of one source row (3 planes x 4 columns x left / right) ...
+  __device__ __forceinline__ void load_taps(const ColTaps& t, int y, float v0[3][4], float v1[3][4]) const {
     const int ro = y * stride;
-    float v0[3][4], v1[3][4];
     if constexpr (PLANE_ELEMS > 0) {
       const float* rowp = elem_ptr(origin[0], ro);   // warp-uniform
 #pragma unroll
@@ -164,11 +167,14 @@ struct CenterRows {
         const float* rowp = elem_ptr(origin[p], ro);   // warp-uniform
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          v0[p][c] = __ldg(byte_ptr(rowp, t.x0[c]));
+            v0[p][c] = __ldg(byte_ptr(rowp, t.x0[c]));
           v1[p][c] = __ldg(byte_ptr(rowp, t.x1[c]));
         }
       }
     }
+  }
+  // ... and their horizontal interpolation
+  __device__ __forceinline__ void lerp_taps(const ColTaps& t, const float v0[3][4], const float v1[3][4], f32x2 s[2], f32x2 cc[4]) const {
     float w0[4], w1[4];
     upk2(t.w0[0], w0[0], w0[1]); upk2(t.w0[1], w0[2], w0[3]);
     upk2(t.w1[0], w1[0], w1[1]); upk2(t.w1[1], w1[2], w1[3]);
@@ -179,34 +185,10 @@ struct CenterRows {
     for (int c = 0; c < 4; ++c)
       cc[c] = lerp_h2(pk2(v0[1][c], v0[2][c]), pk2(v1[1][c], v1[2][c]), pk2(w0[c], w0[c]), pk2(w1[c], w1[c]));
   }
-  // L1 prefetch of the source rows the NEXT output row will need and the cache does not hold (no registers, no
-  // scoreboard): stage 1 is latency-bound (4 warps per sub-partition, 24 dependent taps per new source row), so the
-  // L2 round trip of the next row is started one output row early.  One prefetch per column and plane: the right tap
-  // shares the sector of the left one in all but 1 of 8 positions.
-  __device__ __forceinline__ void prefetch_next(const ColTaps& t, const AxisTap& v) const {
-#ifdef UNMORE_CENTER_PREFETCH
-    auto pf = [&](int y) {
-      const int ro = y * stride;
-      if constexpr (PLANE_ELEMS > 0) {
-        const float* rowp = elem_ptr(origin[0], ro);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float* a0 = byte_ptr(rowp, t.x0[c]);
-#pragma unroll
-          for (int p = 0; p < 3; ++p) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + p * PLANE_ELEMS));
-        }
-      } else {
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const float* rowp = elem_ptr(origin[p], ro);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) asm volatile("prefetch.global.L1 [%0];" ::"l"(byte_ptr(rowp, t.x0[c])));
-        }
-      }
-    };
-    if (v.i0 != cy0 && v.i0 != cy1) pf(v.i0);
-    if (v.i1 != v.i0 && v.i1 != cy1 && v.i1 != cy0) pf(v.i1);
-#endif
+  __device__ __forceinline__ void hrows(const ColTaps& t, int y, f32x2 s[2], f32x2 cc[4]) const {
+    float v0[3][4], v1[3][4];
+    load_taps(t, y, v0, v1);
+    lerp_taps(t, v0, v1, s, cc);
   }
   // s[c] = sdf of column lane + 32c; ab[c] = (c_row, c_col) of that column
   __device__ __forceinline__ void row(const ColTaps& t, const AxisTap& v, float s[4], f32x2 ab[4]) {
@@ -251,7 +233,7 @@ struct CenterTileRows {
 // PLANE_ELEMS: 0 = any field size / channel order; H*W = the three channels are consecutive planes of a field
 // of exactly that size (the COCO-val shape the batch path runs on), see MultiPlaneRows.
 constexpr int kSpecPlaneElems = 480 * 640;
-template <bool ANALYZE_CC, int PLANE_ELEMS>
+template <bool ANALYZE_CC, int PLANE_ELEMS, bool ROW_SKIP>
 __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CenterSmem& sm = *reinterpret_cast<CenterSmem*>(smem_raw);
@@ -330,65 +312,100 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       float cabs = 0.f;  // max |center field| over the tile (>= the staged window's): scales the fp32 screening margin
       // staging predicates of this lane's four columns lane + 32c: columns 32..95 are always inside the window
       const bool col_in[4] = {lane >= kWinLo, true, true, lane + 96 < kWinHi};   // [1], [2] unused: always inside
-      // shared addresses of this warp's first row: staging slot of column `lane`, mask words of the row
+      // Rows are resampled in two phases (kLattice).  Phase 0: the eight LATTICE rows 8, 24, ..., 120, one per warp.
+      // A pixel survives the 25x25 erosion only if every row within 12 of it carries a run of 25 set columns
+      // around it, and every window of 25 rows contains a lattice row: a lattice row WITHOUT any such run rules out
+      // all survivors within 12 rows of it.  That leaves a row range [rmin, rmax] that can hold survivors (often
+      // none: the proposal passes with max 0), and only rows rmin-12 .. rmax+12 are resampled in phase 1 — the
+      // erosion of [rmin, rmax] reads nothing else, and the correlation reads the staged field within 2 rows of a
+      // survivor.  Exact: every value that is computed is computed by the same arithmetic, the rest is never read.
+      // --analyze_cc needs the whole union mask (components of passing proposals) and keeps the single full pass;
+      // so does the second pass over the split halves (launch_center): they are cut through their object, few of
+      // their rows can be skipped and the extra phase costs more than it saves there (+5% measured).
+      constexpr bool kLattice = ROW_SKIP && !ANALYZE_CC && PLANE_ELEMS >= 0;
+      constexpr int kLatFirst = 8, kLatStride = 16, kLatRows = kCrop / kLatStride;
       constexpr int kRowsPerWarp = (kCrop + kCenterWarps - 1) / kCenterWarps;
-      const int row_lo = warp * kRowsPerWarp, row_hi = min(kCrop, row_lo + kRowsPerWarp);
-      unsigned stage_addr = smem_addr(&sm.c[0]) + (unsigned)(((row_lo - kWinLo) * kWinStride + (lane - kWinLo)) * 8);
-      unsigned mask_addr = smem_addr(&sm.mask[0][0]) + 16u * (unsigned)row_lo;
+      int i_begin, i_end, i_step;
+      if constexpr (kLattice) { i_begin = kLatFirst + kLatStride * warp; i_end = kCrop; i_step = kLatStride * kCenterWarps; }
+      else { i_begin = warp * kRowsPerWarp; i_end = min(kCrop, i_begin + kRowsPerWarp); i_step = 1; }
+      int rmin = kErode, rmax = kCrop - kErode - 1;   // rows that can hold survivors
+      bool no_survivors = false;
+      // shared addresses of row 0: staging slot of column `lane`, mask words of the row
+      const unsigned stage_base = smem_addr(&sm.c[0]) + (unsigned)(((0 - kWinLo) * kWinStride + (lane - kWinLo)) * 8);
+      const unsigned mask_base = smem_addr(&sm.mask[0][0]);
       const bool lane0 = lane == 0;
-      // the vertical taps of the warp's rows are computed ONCE, one row per lane, and handed out by shuffle: the
-      // I2F / FFMA / F2I / I2F chain of axis_tap no longer sits in front of every row's loads
-#ifndef UNMORE_CENTER_NO_TAP_SHFL
-      const AxisTap my_tap = axis_tap(scale_y, min(row_lo + lane % kRowsPerWarp, kCrop - 1), in_h);
-#endif
-      for (int i = row_lo; i < row_hi; ++i, stage_addr += kWinStride * 8, mask_addr += 16) {
-        const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
-#ifndef UNMORE_CENTER_NO_TAP_SHFL
-        AxisTap v;
-        v.i0 = __shfl_sync(kFullMask, my_tap.i0, i - row_lo);
-        v.l1 = __shfl_sync(kFullMask, my_tap.l1, i - row_lo);
-        v.i1 = min(v.i0 + 1, in_h - 1);
-        v.l0 = __fsub_rn(1.f, v.l1);
-#else
-        const AxisTap v = axis_tap(scale_y, i, in_h);
-#endif
-        float s[4];
-        f32x2 ab[4];
-        if constexpr (PLANE_ELEMS < 0) trows.row(lane, i, s, ab);
-        else {
-          rows.row(taps, v, s, ab);
-          if (i + 1 < row_hi) rows.prefetch_next(taps, axis_tap(scale_y, i + 1, in_h));
-        }
-        uint32_t word[4];
+#pragma unroll 1
+      for (int phase = 0; phase < (kLattice ? 2 : 1); ++phase) {
+        // the vertical taps of the warp's rows are computed ONCE, one row per lane, and handed out by shuffle: the
+        // I2F / FFMA / F2I / I2F chain of axis_tap no longer sits in front of every row's loads
+        const AxisTap my_tap = axis_tap(scale_y, min(i_begin + lane * i_step, kCrop - 1), in_h);
+        int j = 0;
+        for (int i = i_begin; i < i_end; i += i_step, ++j) {
+          if (kLattice && phase == 1 && (i & (kLatStride - 1)) == kLatFirst) continue;   // done in phase 0
+          const bool row_in = i >= kWinLo && i < kWinHi;   // warp-uniform
+          const unsigned stage_addr = stage_base + (unsigned)(i * (kWinStride * 8));
+          const unsigned mask_addr = mask_base + 16u * (unsigned)i;
+          AxisTap v;
+          v.i0 = __shfl_sync(kFullMask, my_tap.i0, j);
+          v.l1 = __shfl_sync(kFullMask, my_tap.l1, j);
+          v.i1 = min(v.i0 + 1, in_h - 1);
+          v.l0 = __fsub_rn(1.f, v.l1);
+          float s[4];
+          f32x2 ab[4];
+          if constexpr (PLANE_ELEMS < 0) trows.row(lane, i, s, ab);
+          else rows.row(taps, v, s, ab);
+          uint32_t word[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
-          // equivalent threshold on the squared norm
-          float a2, b2, a, b;
-          upk2(mul2(ab[c], ab[c]), a2, b2);
-          upk2(ab[c], a, b);
-          const float sq = __fadd_rn(a2, b2);
-          const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
-          word[c] = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
-#ifdef UNMORE_CENTER_CABS_EXACT
-          cabs = fmaxf(cabs, fmaxf(fabsf(a), fabsf(b)));
-#else
-          cabs = fmaxf(cabs, sq);   // max of the squared norms: sqrt of it bounds max(|a|, |b|) (one instruction instead of three)
-#endif
+          for (int c = 0; c < 4; ++c) {
+            // ||c|| > 0.5 exactly as torch.norm (round(a*a) + round(b*b), IEEE sqrt), via the
+            // equivalent threshold on the squared norm
+            float a2, b2;
+            upk2(mul2(ab[c], ab[c]), a2, b2);
+            const float sq = __fadd_rn(a2, b2);
+            const bool on = (s[c] > UNMORE_SIGMOID_HALF_THRESHOLD) || (sq > UNMORE_NORM_HALF_SQ_THRESHOLD);
+            word[c] = __ballot_sync(kFullMask, on);  // columns 32c .. 32c+31, LSB = lowest
+            cabs = fmaxf(cabs, sq);   // max of the squared norms: sqrt of it bounds max(|a|, |b|) (one instruction instead of three)
+          }
+          st_shared_b32_if<0>(lane0, mask_addr, word[0]);
+          st_shared_b32_if<4>(lane0, mask_addr, word[1]);
+          st_shared_b32_if<8>(lane0, mask_addr, word[2]);
+          st_shared_b32_if<12>(lane0, mask_addr, word[3]);
+          st_shared_b64_if<0>(row_in && col_in[0], stage_addr, ab[0]);
+          st_shared_b64_if<256>(row_in, stage_addr, ab[1]);
+          st_shared_b64_if<512>(row_in, stage_addr, ab[2]);
+          st_shared_b64_if<768>(row_in && col_in[3], stage_addr, ab[3]);
         }
-        st_shared_b32_if<0>(lane0, mask_addr, word[0]);
-        st_shared_b32_if<4>(lane0, mask_addr, word[1]);
-        st_shared_b32_if<8>(lane0, mask_addr, word[2]);
-        st_shared_b32_if<12>(lane0, mask_addr, word[3]);
-        st_shared_b64_if<0>(row_in && col_in[0], stage_addr, ab[0]);
-        st_shared_b64_if<256>(row_in, stage_addr, ab[1]);
-        st_shared_b64_if<512>(row_in, stage_addr, ab[2]);
-        st_shared_b64_if<768>(row_in && col_in[3], stage_addr, ab[3]);
-      }
-      cabs = warp_max(cabs);
-#ifndef UNMORE_CENTER_CABS_EXACT
-      cabs = __fmul_rn(__fsqrt_ru(cabs), 1.000001f);   // an upper bound of max |center field| is all the margin needs
+        if (kLattice && phase == 0) {
+          __syncthreads();
+          // every warp derives the same row range from the lattice rows (no second barrier, no broadcast)
+          bool alive_row = false;
+          if (lane < kLatRows) {
+            u128 m = load_row(sm.mask[kLatFirst + kLatStride * lane]);
+            m &= m >> 1; m &= m >> 2; m &= m >> 4; m &= m >> 8; m &= m >> 9;   // bit j: columns j .. j+24 set
+            alive_row = m != 0;
+          }
+          const unsigned alive = __ballot_sync(kFullMask, alive_row);
+          unsigned long long klo = 0, khi = 0;   // rows within kErode of a dead lattice row
+#pragma unroll
+          for (int k = 0; k < kLatRows; ++k) {
+            const int l = kLatFirst + kLatStride * k, a = l - kErode < 0 ? 0 : l - kErode, b = l + kErode > kCrop - 1 ? kCrop - 1 : l + kErode;
+            unsigned long long lo = 0, hi = 0;
+            for (int r = a; r <= b; ++r) { if (r < 64) lo |= 1ull << r; else hi |= 1ull << (r - 64); }   // folds to constants
+            if (!((alive >> k) & 1u)) { klo |= lo; khi |= hi; }
+          }
+          const unsigned long long clo = ~klo & (~0ull << kErode), chi = ~khi & (~0ull >> kErode);   // rows 12..63, 64..115
+          if (!(clo | chi)) { no_survivors = true; break; }
+#if UNMORE_CENTER_LATTICE != 2   // 2: timing-only, pre-pass without skipping
+          rmin = clo ? __ffsll((long long)clo) - 1 : 63 + __ffsll((long long)chi);
+          rmax = chi ? 127 - __clzll((long long)chi) : 63 - __clzll((long long)clo);
 #endif
+          const int rlo = rmin - kErode, n = rmax + kErode + 1 - rlo, per = (n + kCenterWarps - 1) / kCenterWarps;
+          i_begin = rlo + warp * per; i_end = min(rlo + n, i_begin + per); i_step = 1;
+        }
+      }
+      if (!no_survivors) {
+      cabs = warp_max(cabs);
+      cabs = __fmul_rn(__fsqrt_ru(cabs), 1.000001f);   // an upper bound of max |center field| is all the margin needs
       if (lane == 0) sm.red_f[warp] = cabs;
       __syncthreads();
       locate_next();
@@ -404,7 +421,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       __syncthreads();
       if (tid < kCrop) {
         u128 e = 0;
-        if (tid >= kErode && tid < kCrop - kErode) {
+        if (tid >= rmin && tid <= rmax) {   // rows outside cannot hold survivors (and their neighbours may not have been resampled)
           e = ~(u128)0;
 #pragma unroll 5
           for (int d = -kErode; d <= kErode; ++d) e &= load_row(sm.hrun[tid + d]);
@@ -580,6 +597,7 @@ __global__ void __launch_bounds__(kCenterThreads, 2) center_kernel(const CenterP
       }
 #endif
 #endif
+      }   // !no_survivors
     }
     if (tid == 0) {
       // amax over the whole map: pixels outside the eroded mask contribute 0
@@ -762,12 +780,12 @@ int launch_components(const unsigned char* masks, int B, int* counts, int* boxes
   return (int)cudaGetLastError();
 }
 
-template <bool CC, int PE>
+template <bool CC, int PE, bool RS = false>
 static int launch_center_t(const CenterParams& p, int num_sms, cudaStream_t stream) {
   // function attributes are per device: set on every launch (microseconds), no cached state
-  cudaError_t e = cudaFuncSetAttribute(center_kernel<CC, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
+  cudaError_t e = cudaFuncSetAttribute(center_kernel<CC, PE, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CenterSmem));
   if (e != cudaSuccess) return (int)e;
-  center_kernel<CC, PE><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
+  center_kernel<CC, PE, RS><<<num_sms * 2, kCenterThreads, sizeof(CenterSmem), stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -775,6 +793,9 @@ int launch_center(const CenterParams& p, int num_sms, cudaStream_t stream) {
   if (p.tiles) return p.cc_counts ? launch_center_t<true, -1>(p, num_sms, stream) : launch_center_t<false, -1>(p, num_sms, stream);
   const bool spec = p.H * p.W == kSpecPlaneElems && p.ch_crow == p.ch_sdf + 1 && p.ch_ccol == p.ch_sdf + 2;
   if (p.cc_counts) return spec ? launch_center_t<true, kSpecPlaneElems>(p, num_sms, stream) : launch_center_t<true, 0>(p, num_sms, stream);
+  // row skipping (the lattice pre-pass) pays on the loose proposals of the first pass — the one that asks for split boxes
+  if (UNMORE_CENTER_LATTICE && p.splits)
+    return spec ? launch_center_t<false, kSpecPlaneElems, true>(p, num_sms, stream) : launch_center_t<false, 0, true>(p, num_sms, stream);
   return spec ? launch_center_t<false, kSpecPlaneElems>(p, num_sms, stream) : launch_center_t<false, 0>(p, num_sms, stream);
 }
 

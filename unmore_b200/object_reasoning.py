@@ -513,7 +513,7 @@ class Object_Discovery:
         if stats is not None:
             stats.update(existence_in=counts, pass1=c1, split=sc, split_kept=c2, refine_in=rc, refine_rounds=rounds,
                          label1=fc, kept=kc, existence_scores=ex, refine_boxes=rb, refine_labels=lab,
-                         refine_in_boxes=refine_in, pass1_boxes=p1, argmax1=am1)
+                         refine_in_boxes=refine_in, pass1_boxes=p1, argmax1=am1, pass2_boxes=p2, pass2=c2)
         return kb, kc
 
     def main_object_discovery(self, images=None, image_ids=None, proposals=None) -> Dict[int, np.ndarray]:
