@@ -14,9 +14,8 @@
 //     oracle/oracle.py::_aa_pass): t = s0*w0; then groups of four taps with separate multiply and add; the
 //     remaining (n-1) mod 4 taps with a fused multiply-add.
 //
-// Two kernels with the intermediate in a caller-provided scratch buffer: this is a unit-op path (tiles for
-// inspection / for unmore_update_bbox_from_tiles), not the fused hot path, so it is written for exactness and
-// generality (any window size, any output size) rather than speed.  One thread per output element.
+// Two kernels with the intermediate in a caller-provided scratch buffer: this is the tile path (tiles for the
+// *_from_tiles stages), not the fused hot path.
 #include "resample_aa.cuh"
 #include "unmore_internal.h"
 
@@ -34,8 +33,41 @@ struct AaCropParams {
   float* scratch;  // [n_img * cap * n_ch, H, 128]
 };
 
+// Weights of one output index, normalised exactly as aa_dot does (sequential fp32 sum, then r / total).
+__device__ __forceinline__ void aa_weights(const AaAxis& a, int i, int& xmin, int& n, float* w, int stride, int max_taps) {
+  float center;
+  a.span(i, center, xmin, n);
+  if (n <= 0 || n > max_taps) return;
+  float total = 0.f;
+  for (int k = 0; k < n; ++k) total = __fadd_rn(total, a.raw_weight(xmin + k, center));
+  for (int k = 0; k < n; ++k) {
+    const float r = a.raw_weight(xmin + k, center);
+    w[k * stride] = total != 0.f ? __fdiv_rn(r, total) : r;
+  }
+}
+// aa_dot's accumulation order over a weight table: first tap a product, groups of four with separate multiply and
+// add, the remaining (n-1) mod 4 fused
+template <class Src, class Wt>
+__device__ __forceinline__ float aa_accumulate(int n, Src src, Wt w) {
+  float t = __fmul_rn(src(0), w(0));
+  const int main_taps = ((n - 1) / 4) * 4;
+  int k = 1;
+  for (; k <= main_taps; ++k) t = __fadd_rn(t, __fmul_rn(src(k), w(k)));
+  for (; k < n; ++k) t = __fmaf_rn(src(k), w(k), t);
+  return t;
+}
+
+// Two passes with the intermediate in the caller's scratch buffer, grid = (tile, 8 row slices): the weight tables of
+// a block (the fp64 / division part: ~90% of the instructions of a dot) are built once in shared memory — thread j
+// the horizontal weights of column j, the first threads the vertical weights of the block's output rows.  Windows
+// more than ~11x the tile size in a dimension (more than kAaMaxTaps taps) take aa_dot directly, the same arithmetic.
+// (A single fused kernel with the intermediate in a per-column shared ring, one thread per column, was measured
+// slower: 92.7 vs 79.9 ms on the profile workload — too little parallelism per tile to hide the tap loads.)
+constexpr int kAaMaxTaps = 24, kAaSlices = 8;
+
 // pass 1: T[tile][y][j] = sum_x window[y][x] * wx_j[x] for every row y of the crop window
-__global__ void __launch_bounds__(128) aa_crop_h_kernel(const AaCropParams p) {
+__global__ void __launch_bounds__(kCrop) aa_crop_h_kernel(const AaCropParams p) {
+  __shared__ float wh[kAaMaxTaps][kCrop];   // [tap][column]: thread j reads its own column
   const long long tile = blockIdx.x;             // (row, channel)
   const int k = (int)(tile % p.n_ch);
   const size_t row = (size_t)(tile / p.n_ch);
@@ -50,14 +82,23 @@ __global__ void __launch_bounds__(128) aa_crop_h_kernel(const AaCropParams p) {
   const float* plane = p.fields + ((size_t)img * p.C + p.ch[k]) * p.H * p.W + (size_t)win.y1 * p.W + win.x1;
   float* T = p.scratch + (size_t)tile * p.H * kCrop;
   const int j = threadIdx.x;
+  int xmin, nx;
+  aa_weights(ax, j, xmin, nx, &wh[0][j], kCrop, kAaMaxTaps);   // column-private: no barrier needed
   for (int y = blockIdx.y; y < win.h(); y += gridDim.y) {
     const float* srow = plane + (size_t)y * p.W;
-    T[(size_t)y * kCrop + j] = aa_dot(ax, j, [&](int x) { return __ldg(srow + x); });
+    float t;
+    if (nx <= 0) t = 0.f;
+    else if (nx > kAaMaxTaps) t = aa_dot(ax, j, [&](int x) { return __ldg(srow + x); });
+    else t = aa_accumulate(nx, [&](int q) { return __ldg(srow + xmin + q); }, [&](int q) { return wh[q][j]; });
+    T[(size_t)y * kCrop + j] = t;
   }
 }
 
 // pass 2: out[tile][i][j] = sum_y T[tile][y][j] * wy_i[y]
-__global__ void __launch_bounds__(128) aa_crop_v_kernel(const AaCropParams p) {
+__global__ void __launch_bounds__(kCrop) aa_crop_v_kernel(const AaCropParams p) {
+  constexpr int kRows = kCrop / kAaSlices;   // output rows of one block: blockIdx.y + kAaSlices * r
+  __shared__ float wv[kRows][kAaMaxTaps];
+  __shared__ int vmin[kRows], vn[kRows];
   const long long tile = blockIdx.x;
   const int k = (int)(tile % p.n_ch);
   const size_t row = (size_t)(tile / p.n_ch);
@@ -74,9 +115,21 @@ __global__ void __launch_bounds__(128) aa_crop_v_kernel(const AaCropParams p) {
   }
   AaAxis ay;
   ay.init(win.h(), kCrop);
+  if (j < kRows) {
+    int ymin, ny;
+    aa_weights(ay, blockIdx.y + kAaSlices * j, ymin, ny, &wv[j][0], 1, kAaMaxTaps);
+    vmin[j] = ymin; vn[j] = ny;
+  }
+  __syncthreads();
   const float* T = p.scratch + (size_t)tile * p.H * kCrop;
-  for (int i = blockIdx.y; i < kCrop; i += gridDim.y)
-    o[i * kCrop + j] = aa_dot(ay, i, [&](int y) { return T[(size_t)y * kCrop + j]; });
+  for (int r = 0; r < kRows; ++r) {
+    const int i = blockIdx.y + kAaSlices * r, ymin = vmin[r], n = vn[r];
+    float t;
+    if (n <= 0) t = 0.f;
+    else if (n > kAaMaxTaps) t = aa_dot(ay, i, [&](int y) { return T[(size_t)y * kCrop + j]; });
+    else t = aa_accumulate(n, [&](int q) { return T[(size_t)(ymin + q) * kCrop + j]; }, [&](int q) { return wv[r][q]; });
+    o[i * kCrop + j] = t;
+  }
 }
 
 int launch_crop_resize_aa(const float* fields, int n_img, int C, int H, int W, const int* channels, int n_ch,
@@ -88,7 +141,7 @@ int launch_crop_resize_aa(const float* fields, int n_img, int C, int H, int W, c
   p.fields = fields; p.C = C; p.H = H; p.W = W; p.n_ch = n_ch;
   for (int i = 0; i < n_ch; ++i) p.ch[i] = channels[i];
   p.boxes = boxes; p.boxes_f64 = boxes_f64; p.counts = counts; p.cap = cap; p.n_img = n_img; p.out = out; p.scratch = scratch;
-  dim3 grid((unsigned)tiles, 8);
+  dim3 grid((unsigned)tiles, kAaSlices);
   aa_crop_h_kernel<<<grid, kCrop, 0, stream>>>(p);
   int e = (int)cudaGetLastError();
   if (e) return e;
