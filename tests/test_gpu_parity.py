@@ -506,7 +506,7 @@ def _random_masks(k, H, W, seed):
     m = np.zeros((k, H, W), dtype=np.uint8)
     for i in range(k):
         cy, cx = rng.uniform(0, H), rng.uniform(0, W)
-        ry, rx = rng.uniform(8, H / 3), rng.uniform(8, W / 3)
+        ry, rx = rng.uniform(min(8, H / 3), max(8, H / 3)), rng.uniform(min(8, W / 3), max(8, W / 3))
         m[i] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) < 1
     m[k // 2] = m[k // 3]          # exact duplicate
     m[k - 1] = 0                   # empty mask
@@ -531,17 +531,27 @@ def test_mask_pack_and_mask_nms(dev, ops, W):
     assert np.array_equal(keep, O.mask_nms_dense(dense, scores, 0.1))
 
 
-@pytest.mark.parametrize("W", [640, 100])
-def test_rle_from_packed_masks(dev, ops, W):
+@pytest.mark.parametrize("H,W", [(96, 640), (96, 100), (75, 100), (480, 640), (33, 31), (1, 40), (40, 1), (64, 33)])
+def test_rle_from_packed_masks(dev, ops, H, W):
     """a16 binary_mask_to_rle: GPU run lengths + host string against the restated codec; decode
-    round trip back to the dense mask."""
+    round trip back to the dense mask.  Heights that are / are not multiples of the 32-row transpose block,
+    single-row and single-column masks, all-ones, checkerboards (a run per pixel) and columns that end / start set."""
     from unmore_b200 import rle
-    H, k = 96, 40
+    k = 40 if H * W < 100000 else 12
     dense = _random_masks(k, H, W, seed=9)
     dense[3] = 1                                   # all ones: zero-length leading run
+    dense[4] = 0
     dense[4, ::2, ::2] = 1                         # many short runs
+    dense[5] = (np.add.outer(np.arange(H), np.arange(W)) & 1).astype(dense.dtype)   # checkerboard
+    dense[6] = 0
+    dense[6, -1, :] = 1                            # last row set: every column ends with a one ...
+    dense[7] = 0
+    dense[7, 0, :] = 1                             # ... / starts with a one
+    dense[8] = 0
+    dense[8, -1, :] = 1; dense[8, 0, :] = 1        # runs that continue across the column boundary
+    dense[9] = 0
     packed = ops.mask_pack(torch.tensor(dense, device=dev))
-    enc = rle.encode_packed(packed, W, max_runs=256)   # forces the grow-and-retry path for mask 4
+    enc = rle.encode_packed(packed, W, max_runs=256)   # forces the grow-and-retry path for the dense patterns
     for i in range(k):
         c = O.rle_counts_np(dense[i])
         assert enc[i] == {"size": [H, W], "counts": O.rle_to_string(c)}, i

@@ -259,16 +259,114 @@ __global__ void __launch_bounds__(32) greedy_scan_kernel(const unsigned long lon
 
 // ---- COCO run-length counts (pycocotools maskApi.c rleEncode semantics) ----------------------
 // Column-major scan (t = x*H + y); counts[0] is the length of the leading run of zeros (possibly 0),
-// then alternating one / zero runs.  One CTA per mask: each thread scans a contiguous range of t,
-// change positions are ranked with a block scan and staged in shared memory, counts are their
-// differences.  n_runs_out reports the true number of runs even when it exceeds max_runs (then
-// nothing is written for that mask and the caller falls back to a larger buffer).
+// then alternating one / zero runs.  n_runs_out reports the true number of runs even when it exceeds
+// max_runs (then nothing is written for that mask and the caller falls back to a larger buffer).
+//
+// One CTA per mask, word-parallel: the bit-packed rows are staged in shared memory (coalesced, odd row
+// stride), transposed in 32x32 bit blocks with warp ballots into column-major words T[x][j] (bit b = row
+// 32j + b of column x), and the run boundaries are the set bits of T ^ (T << 1 | last bit of the previous
+// word of the column-major stream).  Each thread owns a contiguous range of stream words: a block scan of
+// the change counts and of the last change position gives every thread its output slot and the position
+// its first run starts from; the counts are then written straight to global memory.  ~30 k warp
+// instructions per 480x640 mask; the bit-serial form below (one divide + one load per bit, twice) needs
+// ~290 k and is kept for masks whose two shared arrays do not fit.
 constexpr int kRleThreads = 256;
-constexpr int kRleMaxRuns = 8192;   // change positions staged in 32 KB of shared memory
+constexpr int kRleMaxRuns = 8192;   // bit-serial fallback only: change positions staged in 32 KB of shared memory
+constexpr int kRleMaxDynSmem = 200 * 1024;
 
 __global__ void __launch_bounds__(kRleThreads) rle_counts_kernel(const uint32_t* __restrict__ masks, int K, int H, int W,
                                                                   int Wp, int max_runs, uint32_t* __restrict__ counts,
                                                                   int* __restrict__ n_runs) {
+  extern __shared__ uint32_t rle_smem[];
+  __shared__ int wsum[kRleThreads / 32], wlast[kRleThreads / 32];
+  const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Hw = (H + 31) >> 5, stride = Wp | 1;
+  uint32_t* rows = rle_smem;                       // [H][stride]
+  uint32_t* T = rle_smem + (size_t)H * stride;     // [W][Hw]
+  const uint32_t* m = masks + (size_t)k * H * Wp;
+  for (int idx = tid; idx < H * Wp; idx += kRleThreads) {
+    const int y = idx / Wp, w = idx - y * Wp;
+    rows[y * stride + w] = __ldg(m + idx);
+  }
+  __syncthreads();
+  for (int q = warp; q < Hw * Wp; q += kRleThreads / 32) {   // 32 rows x 32 columns per step
+    const int j = q / Wp, w = q - j * Wp, y = 32 * j + lane;
+    const uint32_t word = y < H ? rows[y * stride + w] : 0u;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t bal = __ballot_sync(kFullMask, (word >> b) & 1u);
+      if (lane == b) mine = bal;
+    }
+    const int x = 32 * w + lane;
+    if (x < W) T[x * Hw + j] = mine;
+  }
+  __syncthreads();
+  const int G = W * Hw, N = H * W;
+  const int per = (G + kRleThreads - 1) / kRleThreads;
+  const int g0 = min(tid * per, G), g1 = min(g0 + per, G);
+  const uint32_t tail_mask = (H & 31) ? ((1u << (H & 31)) - 1u) : ~0u;   // valid rows of the last word of a column
+  // boundaries inside stream word g = (x, j): bit b set <=> pixel (x, 32j + b) differs from its predecessor in the scan
+  auto changes = [&](int g, int x, int j) -> uint32_t {
+    const uint32_t t = T[g];
+    uint32_t carry;
+    if (j > 0) carry = T[g - 1] >> 31;
+    else carry = x > 0 ? (T[g - 1] >> ((H - 1) & 31)) & 1u : 0u;     // last row of the previous column; 0 before t = 0
+    return (t ^ ((t << 1) | carry)) & (j == Hw - 1 ? tail_mask : ~0u);
+  };
+  int mine = 0, last = -1;
+  {
+    int x = g0 / Hw, j = g0 - x * Hw;
+    for (int g = g0; g < g1; ++g) {
+      const uint32_t c = changes(g, x, j);
+      if (c) { mine += __popc(c); last = x * H + 32 * j + (31 - __clz(c)); }
+      if (++j == Hw) { j = 0; ++x; }
+    }
+  }
+  int incl = mine, lmax = last;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(kFullMask, incl, o);
+    const int z = __shfl_up_sync(kFullMask, lmax, o);
+    if (lane >= o) { incl += y; lmax = max(lmax, z); }
+  }
+  int prev = __shfl_up_sync(kFullMask, lmax, 1);   // last change before this thread inside the warp
+  if (lane == 0) prev = -1;
+  if (lane == 31) { wsum[warp] = incl; wlast[warp] = lmax; }
+  __syncthreads();
+  int base = 0, total = 0, glast = -1;
+  for (int w = 0; w < kRleThreads / 32; ++w) {
+    if (w < warp) { base += wsum[w]; prev = max(prev, wlast[w]); }
+    total += wsum[w];
+    glast = max(glast, wlast[w]);
+  }
+  const int runs = total + 1;
+  if (tid == 0) n_runs[k] = runs;
+  if (runs > max_runs) return;   // uniform
+  uint32_t* out = counts + (size_t)k * max_runs;
+  int r = base + incl - mine;
+  int pp = prev < 0 ? 0 : prev;   // the first run starts at t = 0
+  {
+    int x = g0 / Hw, j = g0 - x * Hw;
+    for (int g = g0; g < g1; ++g) {
+      uint32_t c = changes(g, x, j);
+      while (c) {
+        const int t = x * H + 32 * j + __ffs((int)c) - 1;
+        c &= c - 1;
+        out[r++] = (uint32_t)(t - pp);
+        pp = t;
+      }
+      if (++j == Hw) { j = 0; ++x; }
+    }
+  }
+  if (tid == 0) out[total] = (uint32_t)(N - (glast < 0 ? 0 : glast));
+}
+
+// bit-serial form: each thread scans a contiguous range of t, change positions are ranked with a block scan and
+// staged in shared memory, counts are their differences
+__global__ void __launch_bounds__(kRleThreads) rle_counts_kernel_serial(const uint32_t* __restrict__ masks, int K, int H, int W,
+                                                                         int Wp, int max_runs, uint32_t* __restrict__ counts,
+                                                                         int* __restrict__ n_runs) {
   __shared__ uint32_t pos[kRleMaxRuns];
   __shared__ int wsum[kRleThreads / 32];
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -318,7 +416,18 @@ __global__ void __launch_bounds__(kRleThreads) rle_counts_kernel(const uint32_t*
 int launch_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs, uint32_t* counts, int* n_runs,
                       cudaStream_t stream) {
   if (K <= 0) return 0;
-  rle_counts_kernel<<<K, kRleThreads, 0, stream>>>(masks, K, H, W, (W + 31) >> 5, max_runs, counts, n_runs);
+  const int Wp = (W + 31) >> 5, Hw = (H + 31) >> 5;
+  const size_t smem = ((size_t)H * (Wp | 1) + (size_t)W * Hw) * sizeof(uint32_t);
+#ifndef UNMORE_RLE_SERIAL
+  if (smem <= (size_t)kRleMaxDynSmem) {
+    // function attributes are per device: set on every launch (microseconds), no cached state
+    cudaError_t e = cudaFuncSetAttribute(rle_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    rle_counts_kernel<<<K, kRleThreads, smem, stream>>>(masks, K, H, W, Wp, max_runs, counts, n_runs);
+    return (int)cudaGetLastError();
+  }
+#endif
+  rle_counts_kernel_serial<<<K, kRleThreads, 0, stream>>>(masks, K, H, W, Wp, max_runs, counts, n_runs);
   return (int)cudaGetLastError();
 }
 

@@ -77,7 +77,7 @@ def encode_packed(packed: torch.Tensor, width: int, max_runs: int = 4096) -> Lis
         return []
     counts, n_runs = ops.mask_rle_counts(packed, width, max_runs)
     n = n_runs.cpu().numpy()
-    limit = 8192   # the kernel stages change positions in shared memory (kRleMaxRuns)
+    limit = 8192   # bound of the device buffer; masks with more runs (pathological) are encoded on the host below
     if max_runs < limit and int(n.max()) > max_runs:
         return encode_packed(packed, width, max_runs=limit)
     c = counts.cpu().numpy().view(np.uint32)
