@@ -509,13 +509,17 @@ def main():
                  torch.empty((chunk, n_prop, 4), dtype=torch.float64, device=dev)) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
-        MAX_RUNS = 1024
+        MAX_RUNS = 2048   # a mask over all 640 columns has up to 1281 runs
         h2d = d2h = d2h_rows = 0
-        n_rle = 0
+        n_rle = rle_off = rle_moff = 0
+        from concurrent.futures import ThreadPoolExecutor
+        reader = ThreadPoolExecutor(max_workers=1)   # the RLE read-back of chunk j overlaps the launches of chunk j + 1
+        rle_len = torch.empty((max(1024, 12 * n_img),), dtype=torch.int32).pin_memory()   # ~7 kept masks per image here
+        rle_arena = torch.empty((rle_len.shape[0] * 512,), dtype=torch.int32).pin_memory()   # ~200 runs per mask here
 
         def e2e_step(with_rle=True):
-            nonlocal h2d, d2h, d2h_rows, n_rle
-            h2d = d2h = d2h_rows = n_rle = 0
+            nonlocal h2d, d2h, d2h_rows, n_rle, rle_off, rle_moff
+            h2d = d2h = d2h_rows = n_rle = rle_off = rle_moff = 0
             rows = ops.detection_rows(max_rows, dev)
             host_rle = []
             chunks = list(range(0, n_img, chunk))
@@ -534,11 +538,13 @@ def main():
 
             rle_stream = side_stream
             done_ev = [torch.cuda.Event() for _ in chunks]
+            futures = []
 
             def read_back(j, r):
                 """COCO run lengths of the kept masks of chunk j (NMS order) on the SIDE stream, then their device -> host
-                read: the host blocks here while the main stream is already running chunk j + 1."""
-                nonlocal d2h, n_rle
+                read into the pinned arena.  Runs on the reader thread: the thread that launches the chunks never waits for it."""
+                nonlocal d2h, n_rle, rle_off, rle_moff
+                torch.cuda.set_device(dev)
                 with torch.cuda.stream(rle_stream):
                     rle_stream.wait_event(done_ev[j])
                     B, cap = r["keep"].shape
@@ -546,15 +552,30 @@ def main():
                     flat = (torch.arange(B, device=dev)[:, None] * cap + r["keep"].clamp_min(0))[valid]
                     km = r["masks"].view(B * cap, Hc, -1).index_select(0, flat)
                     cnt, nr = ops.mask_rle_counts(km, Wc, MAX_RUNS)
-                    hc, hn = cnt.cpu(), nr.cpu()
+                    K = int(nr.numel())
+                    n_max = int(nr.max().item()) if K else 0
+                    if n_max > MAX_RUNS:   # a ragged mask with more runs than the buffer holds: once more, large enough
+                        cnt, nr = ops.mask_rle_counts(km, Wc, 1 << (n_max - 1).bit_length())
+                    # only the run lengths that exist travel: [sum of n_runs] int32 + the K lengths
+                    used = torch.arange(cnt.shape[1], device=dev)[None, :] < nr[:, None]
+                    flat_counts = cnt[used]
+                    T = int(flat_counts.numel())
+                    if rle_off + T <= rle_arena.shape[0] and rle_moff + K <= rle_len.shape[0]:
+                        hc, hn = rle_arena[rle_off:rle_off + T], rle_len[rle_moff:rle_moff + K]
+                        hc.copy_(flat_counts, non_blocking=True)
+                        hn.copy_(nr, non_blocking=True)
+                        rle_off += T
+                        rle_moff += K
+                        rle_stream.synchronize()
+                    else:   # more than the arena was sized for: pageable copies
+                        hc, hn = flat_counts.cpu(), nr.cpu()
                     for t_ in (r["keep"], r["keep_counts"], r["masks"]):
                         t_.record_stream(rle_stream)
                 d2h += hc.numel() * 4 + hn.numel() * 4
-                n_rle += int(hn.numel())
+                n_rle += K
                 host_rle.append((hc, hn))
 
             h2d += issue(0)
-            prev = None
             for j, c0 in enumerate(chunks):
                 c1 = min(c0 + chunk, n_img)
                 if j + 1 < len(chunks):
@@ -565,11 +586,10 @@ def main():
                 ops.pack_detections(image_ids[c0:c1], r["bbox"], r["out"], r["keep_counts"], rows)
                 freed[j % 2].record(torch.cuda.current_stream())
                 done_ev[j].record(torch.cuda.current_stream())
-                if with_rle and prev is not None:
-                    read_back(*prev)
-                prev = (j, r)
-            if with_rle and prev is not None:
-                read_back(*prev)
+                if with_rle:
+                    futures.append(reader.submit(read_back, j, r))
+            for f in futures:
+                f.result()
             g2 = gather_rows(rows)
             m2, t2 = merge_rows(g2)
             hr = m2[: int(t2.item())].cpu()          # device -> host read of the detection rows
@@ -583,10 +603,19 @@ def main():
         reps = max(1, min(args.steps, 2))
         t0 = time.perf_counter()
         for _ in range(reps):
-            e2e_step()
+            last = e2e_step()
         barrier()
         dt = (time.perf_counter() - t0) / reps
         d2h_full, n_rle_full = d2h, n_rle
+        # what was read back is a complete result: every mask's run lengths cover the image, one mask per detection row
+        def _complete(hc, hn):
+            n = hn.numpy().astype(np.int64)
+            if n.size == 0:
+                return True
+            starts = np.concatenate([[0], np.cumsum(n)[:-1]])
+            return int(n.sum()) == hc.numel() and bool((np.add.reduceat(hc.numpy().astype(np.int64), starts) == Hc * Wc).all())
+        rle_ok = all(_complete(hc, hn) for hc, hn in last[1])
+        rle_ok = rle_ok and sum(int(hn.numel()) for _, hn in last[1]) == (int(last[0].shape[0]) if world == 1 else n_rle)
         e2e_step(with_rle=False)
         barrier()
         t0 = time.perf_counter()
@@ -601,10 +630,11 @@ def main():
         e2e = {"value": n_global / dt, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
                "host_pool_images": pool, "ms_per_step": dt * 1e3,
                "result": "detection rows (image_id, x, y, w, h, score) fp64 + COCO RLE run lengths of every kept mask "
-                         f"(unmore_mask_rle_counts, {MAX_RUNS} int32 per mask + its length)",
-               "masks_rle_per_step": n_rle_full,
+                         "(unmore_mask_rle_counts; the existing run lengths of each mask + its length, int32)",
+               "masks_rle_per_step": n_rle_full, "rle_complete": bool(rle_ok),
                "rows_only": {"value": n_global / dt_rows, "ms_per_step": dt_rows * 1e3, "d2h_bytes_per_step": d2h_rows}}
-        del h_fields, bufs
+        reader.shutdown()
+        del h_fields, bufs, rle_arena, rle_len
 
     # ---- configs[2] side measurement (outside the step): mask bit-pack (HBM streaming) and the
     # mask-IoU / box NMS sweep at 1k - 16k masks per image, 480x640
