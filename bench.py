@@ -522,15 +522,19 @@ def main():
             h2d = d2h = d2h_rows = n_rle = rle_off = rle_moff = 0
             rows = ops.detection_rows(max_rows, dev)
             host_rle = []
-            chunks = list(range(0, n_img, chunk))
+            # a short first chunk: its host -> device copy is the only one nothing overlaps
+            chunks, c0 = [], 0
+            while c0 < n_img:
+                c1 = min(n_img, c0 + (max(1, chunk // 4) if c0 == 0 else chunk))
+                chunks.append((c0, c1))
+                c0 = c1
 
             def issue(j):
-                c0 = chunks[j]
-                c1 = min(c0 + chunk, n_img)
+                c0, c1 = chunks[j]
                 fb, pb = bufs[j % 2]
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[j % 2])
-                    p0 = c0 % pool
+                    p0 = min(c0 % pool, pool - (c1 - c0))   # the host pool may hold fewer images than the step (they repeat)
                     fb[: c1 - c0].copy_(h_fields[p0:p0 + (c1 - c0)], non_blocking=True)
                     pb[: c1 - c0].copy_(h_props[c0:c1], non_blocking=True)
                     ready[j % 2].record(copy_stream)
@@ -576,8 +580,7 @@ def main():
                 host_rle.append((hc, hn))
 
             h2d += issue(0)
-            for j, c0 in enumerate(chunks):
-                c1 = min(c0 + chunk, n_img)
+            for j, (c0, c1) in enumerate(chunks):
                 if j + 1 < len(chunks):
                     h2d += issue(j + 1)
                 torch.cuda.current_stream().wait_event(ready[j % 2])
