@@ -107,6 +107,39 @@ def test_shard_ranges_cover_everything():
         assert shard_range(n, w - 1, w)[1] == n
 
 
+def test_merge_rows_properties():
+    """merge_rows on stacked per-rank buffers (what the collective delivers), seeded random shapes: the valid rows
+    come first, stably sorted by image id (rank order, then arrival order inside an image), the padding never leaks,
+    the total is the sum of the headers, and an overflow flag on any rank is seen."""
+    from hypothesis import given, settings, strategies as st
+    from unmore_b200.sharding import merge_rows, overflowed, pack_rows_host
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 5), st.integers(0, 6), st.integers(1, 4), st.integers(0, 2 ** 31 - 1))
+    def check(world, n_img, cap, seed):
+        g = torch.Generator().manual_seed(seed)
+        bufs, ref = [], []
+        for r in range(world):
+            ids = torch.randint(0, 9, (n_img,), generator=g).sort().values + 2 ** 30      # ranks may even share an image id
+            counts = torch.randint(0, cap + 1, (n_img,), generator=g).to(torch.int32)
+            boxes = torch.rand((n_img, cap, 4), generator=g, dtype=torch.float64)
+            scores = torch.rand((n_img, cap), generator=g, dtype=torch.float64)
+            bufs.append(pack_rows_host(ids, boxes, counts, scores, max_rows=n_img * cap + 3))
+            for j in range(n_img):
+                for k in range(int(counts[j])):
+                    ref.append((int(ids[j]), r, len(ref), torch.cat([ids[j:j + 1].double(), boxes[j, k], scores[j, k:k + 1]])))
+        gathered = torch.stack(bufs)
+        rows, total = merge_rows(gathered)
+        assert int(total) == len(ref) and not bool(overflowed(gathered))
+        ref.sort(key=lambda t: (t[0], t[1], t[2]))
+        if ref:
+            assert torch.equal(rows[: len(ref)], torch.stack([t[3] for t in ref]))
+        gathered[world - 1, 0, 1] = 1
+        assert bool(overflowed(gathered))
+
+    check()
+
+
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
