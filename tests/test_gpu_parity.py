@@ -531,13 +531,13 @@ def test_mask_pack_and_mask_nms(dev, ops, W):
     assert np.array_equal(keep, O.mask_nms_dense(dense, scores, 0.1))
 
 
-@pytest.mark.parametrize("H,W", [(96, 640), (96, 100), (75, 100), (480, 640), (33, 31), (1, 40), (40, 1), (64, 33)])
+@pytest.mark.parametrize("H,W", [(96, 640), (96, 100), (75, 100), (480, 640), (33, 31), (1, 40), (40, 1), (64, 33), (1000, 1024), (1500, 1600)])
 def test_rle_from_packed_masks(dev, ops, H, W):
     """a16 binary_mask_to_rle: GPU run lengths + host string against the restated codec; decode
     round trip back to the dense mask.  Heights that are / are not multiples of the 32-row transpose block,
     single-row and single-column masks, all-ones, checkerboards (a run per pixel) and columns that end / start set."""
     from unmore_b200 import rle
-    k = 40 if H * W < 100000 else 12
+    k = 40 if H * W < 100000 else 12   # (1000, 1024): transposed words only in shared memory; (1500, 1600): bit-serial fallback
     dense = _random_masks(k, H, W, seed=9)
     dense[3] = 1                                   # all ones: zero-length leading run
     dense[4] = 0

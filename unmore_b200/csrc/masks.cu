@@ -274,6 +274,9 @@ constexpr int kRleThreads = 256;
 constexpr int kRleMaxRuns = 8192;   // bit-serial fallback only: change positions staged in 32 KB of shared memory
 constexpr int kRleMaxDynSmem = 200 * 1024;
 
+// STAGE_ROWS = false: the rows are read from global memory by the transpose itself (strided, one sector per lane) —
+// for masks whose rows + transposed words do not fit the shared memory together (1024x1024: 135 + 131 KB)
+template <bool STAGE_ROWS>
 __global__ void __launch_bounds__(kRleThreads) rle_counts_kernel(const uint32_t* __restrict__ masks, int K, int H, int W,
                                                                   int Wp, int max_runs, uint32_t* __restrict__ counts,
                                                                   int* __restrict__ n_runs) {
@@ -281,17 +284,19 @@ __global__ void __launch_bounds__(kRleThreads) rle_counts_kernel(const uint32_t*
   __shared__ int wsum[kRleThreads / 32], wlast[kRleThreads / 32];
   const int k = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Hw = (H + 31) >> 5, stride = Wp | 1;
-  uint32_t* rows = rle_smem;                       // [H][stride]
-  uint32_t* T = rle_smem + (size_t)H * stride;     // [W][Hw]
+  uint32_t* rows = rle_smem;                                            // [H][stride]
+  uint32_t* T = rle_smem + (STAGE_ROWS ? (size_t)H * stride : 0);       // [W][Hw]
   const uint32_t* m = masks + (size_t)k * H * Wp;
-  for (int idx = tid; idx < H * Wp; idx += kRleThreads) {
-    const int y = idx / Wp, w = idx - y * Wp;
-    rows[y * stride + w] = __ldg(m + idx);
+  if constexpr (STAGE_ROWS) {
+    for (int idx = tid; idx < H * Wp; idx += kRleThreads) {
+      const int y = idx / Wp, w = idx - y * Wp;
+      rows[y * stride + w] = __ldg(m + idx);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int q = warp; q < Hw * Wp; q += kRleThreads / 32) {   // 32 rows x 32 columns per step
     const int j = q / Wp, w = q - j * Wp, y = 32 * j + lane;
-    const uint32_t word = y < H ? rows[y * stride + w] : 0u;
+    const uint32_t word = y < H ? (STAGE_ROWS ? rows[y * stride + w] : __ldg(m + (size_t)y * Wp + w)) : 0u;
     uint32_t mine = 0;
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
@@ -417,13 +422,19 @@ int launch_rle_counts(const uint32_t* masks, int K, int H, int W, int max_runs, 
                       cudaStream_t stream) {
   if (K <= 0) return 0;
   const int Wp = (W + 31) >> 5, Hw = (H + 31) >> 5;
-  const size_t smem = ((size_t)H * (Wp | 1) + (size_t)W * Hw) * sizeof(uint32_t);
+  const size_t smem_t = (size_t)W * Hw * sizeof(uint32_t), smem = smem_t + (size_t)H * (Wp | 1) * sizeof(uint32_t);
 #ifndef UNMORE_RLE_SERIAL
+  // function attributes are per device: set on every launch (microseconds), no cached state
   if (smem <= (size_t)kRleMaxDynSmem) {
-    // function attributes are per device: set on every launch (microseconds), no cached state
-    cudaError_t e = cudaFuncSetAttribute(rle_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rle_counts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    rle_counts_kernel<<<K, kRleThreads, smem, stream>>>(masks, K, H, W, Wp, max_runs, counts, n_runs);
+    rle_counts_kernel<true><<<K, kRleThreads, smem, stream>>>(masks, K, H, W, Wp, max_runs, counts, n_runs);
+    return (int)cudaGetLastError();
+  }
+  if (smem_t <= (size_t)kRleMaxDynSmem) {
+    cudaError_t e = cudaFuncSetAttribute(rle_counts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+    if (e != cudaSuccess) return (int)e;
+    rle_counts_kernel<false><<<K, kRleThreads, smem_t, stream>>>(masks, K, H, W, Wp, max_runs, counts, n_runs);
     return (int)cudaGetLastError();
   }
 #endif
